@@ -1,0 +1,183 @@
+/*
+ * b2lddmm.h - C ABI of the B200-native registration-to-strain hot path.
+ *
+ * This is the drop-in boundary.  The reference reaches
+ * this path through the Python operator surface of the third-party `lagomorph`
+ * package (imported at /root/reference/modules/trainer/joint_registration_strainmat_LMA.py:5,
+ * reg_trainer.py:4) whose native layer is the pybind11 extension `lagomorph_ext`;
+ * neither is vendored in the reference tree.  Each entry point below names the
+ * lagomorph / lagomorph_ext function it replaces and the reference call site
+ * that consumes its result.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *    name ends in `_host`; tensors are contiguous fp32, layout (P, C, H, W),
+ *    vector fields C = 2 with component 0 along rows (H), 1 along columns (W),
+ *    displacements in pixels.
+ *  - batch broadcast: PI / Pu are either 1 or P (lagomorph broadcasts I or u).
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream ordered;
+ *    no call allocates, frees or synchronises; scratch comes from the caller
+ *    (`*_workspace_bytes` queries).
+ *  - return value: 0 = ok, < 0 = invalid argument (B2_E_*), > 0 = cudaError_t.
+ *    Nothing throws.  b2_error_string() decodes either range.
+ *  - background: 0 = clamp-to-edge (D1 default), 1 = zero.
+ *  - FFT sizes: H and W powers of two in [16, 256] (fluid metric, shooting).
+ */
+#ifndef B2LDDMM_H
+#define B2LDDMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_E_NULL (-1)       /* required pointer is NULL */
+#define B2_E_SHAPE (-2)      /* non-positive or unsupported dimension */
+#define B2_E_BCAST (-3)      /* batch sizes do not broadcast */
+#define B2_E_FFTSIZE (-4)    /* H or W not a supported power of two */
+#define B2_E_PARAM (-5)      /* bad scalar parameter (gamma <= 0, n_sectors, flags...) */
+#define B2_E_WORKSPACE (-6)  /* workspace missing or too small */
+
+#define B2_BG_CLAMP 0
+#define B2_BG_ZERO 1
+
+int b2_version(void);
+const char* b2_error_string(int code);
+
+/* ---- lagomorph.interp  (lagomorph_ext.interp_forward / interp_backward) ----
+ * out(p,c,x) = I(p,c, x + dt*u(p,:,x)), bilinear.  Consumer: 'deformed_source',
+ * joint_registration_strainmat_LMA.py:315; reg_trainer.py:225. */
+int b2_interp_fwd(const float* I, const float* u, float* out,
+                  int64_t P, int64_t PI, int64_t Pu, int64_t C, int64_t H, int64_t W,
+                  float dt, int background, void* stream);
+/* dI (PI,C,H,W) and du (Pu,2,H,W) may each be NULL (gradient not needed).
+ * dI is zero-filled by the call and accumulated with float atomics. */
+int b2_interp_bwd(const float* gout, const float* I, const float* u, float* dI, float* du,
+                  int64_t P, int64_t PI, int64_t Pu, int64_t C, int64_t H, int64_t W,
+                  float dt, int background, void* stream);
+
+/* ---- warp of frames and masks: Sdef = lagomorph.interp(src, u) with src (B,C,H,W) shared by
+ * the T1 frame-pairs of its slice; u (B*T1,2,H,W); out (B*T1,C,H,W).  Replaces the
+ * src.repeat(T1) + interp of the reference path (modules/data/__init__.py:109,
+ * joint_registration_strainmat_LMA.py:315).  dsrc (B,C,H,W) / du may be NULL. */
+int b2_warp_fwd(const float* src, const float* u, float* out, int64_t B, int64_t T1, int64_t C,
+                int64_t H, int64_t W, float dt, int background, void* stream);
+int b2_warp_bwd(const float* gout, const float* src, const float* u, float* dsrc, float* du,
+                int64_t B, int64_t T1, int64_t C, int64_t H, int64_t W, float dt, int background,
+                void* stream);
+
+/* ---- lagomorph.splat ----  transpose of interp in I; wout (P,1,H,W) optional. */
+int b2_splat_fwd(const float* J, const float* u, float* out, float* wout,
+                 int64_t P, int64_t PJ, int64_t Pu, int64_t C, int64_t H, int64_t W,
+                 float dt, int background, void* stream);
+
+/* ---- lagomorph.compose_disp_vel ----  out = interp(u, v, dt) + dt*v,  all (P,2,H,W). */
+int b2_compose_fwd(const float* u, const float* v, float* out,
+                   int64_t P, int64_t H, int64_t W, float dt, int background, void* stream);
+int b2_compose_bwd(const float* gout, const float* u, const float* v, float* du, float* dv,
+                   int64_t P, int64_t H, int64_t W, float dt, int background, void* stream);
+
+/* ---- lagomorph.jacobian_times_vectorfield ----
+ * out = (displacement*I + Dv) w, or its transpose applied to w; central
+ * differences, one-sided at the image edge (D2). */
+int b2_jtv_fwd(const float* v, const float* w, float* out, int64_t P, int64_t H, int64_t W,
+               int displacement, int transpose, void* stream);
+int b2_jtv_bwd(const float* gout, const float* v, const float* w, float* dv, float* dw,
+               int64_t P, int64_t H, int64_t W, int displacement, int transpose, void* stream);
+
+/* ---- lagomorph.Ad_star ----  m = (I + Du)^T (m0 o (id + u)).
+ * bwd needs a (P,2,H,W) float workspace (holds m0 o (id+u)). dm0 is zero-filled. */
+int b2_adstar_fwd(const float* u, const float* m0, float* out,
+                  int64_t P, int64_t H, int64_t W, int background, void* stream);
+int b2_adstar_bwd(const float* gout, const float* u, const float* m0, float* du, float* dm0,
+                  float* workspace, int64_t P, int64_t H, int64_t W, int background, void* stream);
+
+/* ---- lagomorph.FluidMetric.flat / .sharp  (lagomorph_ext.fluid_operator + FFT) ----
+ * L = gamma*I - alpha*Lap - beta*grad div on the periodic grid, applied in the
+ * Fourier domain by an in-kernel shared-memory FFT; inverse != 0 solves (sharp).
+ * Self-adjoint: the backward pass is the same call on the incoming gradient.
+ * May run in place (f == out). */
+int64_t b2_fluid_workspace_bytes(int64_t P, int64_t H, int64_t W);
+int b2_fluid_apply(const float* f, float* out, int64_t P, int64_t H, int64_t W,
+                   float alpha, float beta, float gamma, int inverse,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- sectors ([SPEC]; count/order pinned by DENSE_utils.py:177-295, affine.py:52-87) ----
+ * Host helper: Q20 boundary directions (row, col) for n_sectors wedges. */
+int b2_sector_table_host(int n_sectors, int32_t* table_host /* 2*n_sectors */);
+/* moments (B,3) int64 = {count, sum(row), sum(col)} of mask0 > 0.5; zero-filled by the call. */
+int b2_mask_moments(const float* mask0, int64_t* moments, int64_t B, int64_t H, int64_t W,
+                    void* stream);
+int b2_sector_map_i32(const int64_t* moments, const int32_t* table, int32_t* sector,
+                      int64_t B, int64_t H, int64_t W, int n_sectors, void* stream);
+
+/* ---- strain matrix ([SPEC] SURVEY.md A.7/A.8) ----
+ * u (B,T1,2,H,W), tar (B,T1,H,W) masks, moments (B,3).  S (B,1,n_sectors,n_frames):
+ * per-sector mean Ecc of frame t in column t, columns >= T1 edge-padded, columns
+ * beyond n_frames cropped (align_n_frames_to, DENSE_IO_utils.py:26-46).
+ * counts (B,n_sectors,T1) int32 is optional output (needed by the backward). */
+int b2_strain_sector_fwd(const float* u, const float* tar, const int64_t* moments,
+                         const int32_t* table, float* S, int32_t* counts,
+                         int64_t B, int64_t T1, int64_t H, int64_t W,
+                         int n_sectors, int n_frames, void* stream);
+int b2_strain_sector_bwd(const float* gS, const float* u, const float* tar,
+                         const int64_t* moments, const int32_t* table, const int32_t* counts,
+                         float* du, int64_t B, int64_t T1, int64_t H, int64_t W,
+                         int n_sectors, int n_frames, void* stream);
+
+/* ---- fused geodesic shooting: flat + S x EPDiff_step (+ warp + strain) ----
+ * Replaces m0 = metric.flat(v0); u = lagomorph.expmap(metric, m0, T, num_steps);
+ * Sdef = lagomorph.interp(src, u)  and the strain reduction, i.e. the body of
+ * forward_volume (call site joint_registration_strainmat_LMA.py:307).
+ *
+ * v0 (P,2,H,W) with P = B*T1 ordered slice-major; src (B,1,H,W) frame-0 images
+ * (broadcast over the T1 pairs of a slice; src_per_pair != 0 means src is (P,1,H,W));
+ * tar (P,1,H,W).  Outputs (each may be NULL except u): m0 = flat(v0) 'momentum',
+ * vel = sharp(m0) 'velocity', u = u^S 'displacement', sdef = interp(src,u)
+ * 'deformed_source', S strain matrix (B,1,n_sectors,n_frames; needs moments+table+tar),
+ * traj (num_steps, 2, P, 2, H, W): step-major (u_s, v_s) of every step, for the adjoint. */
+typedef struct b2_shoot_args {
+  const float* v0;
+  const float* src;
+  const float* tar;
+  const int64_t* moments;
+  const int32_t* table;
+  float* m0;
+  float* vel;
+  float* u;
+  float* sdef;
+  float* S;
+  int32_t* counts;
+  float* traj;
+  int64_t B, T1, H, W;
+  int32_t num_steps;
+  int32_t src_per_pair;
+  int32_t v0_is_momentum;  /* != 0: `v0` already holds m0 (lagomorph.expmap(metric, m0)); flat is skipped,
+                              the m0 output is not written and vel = sharp(m0) */
+  int32_t n_sectors, n_frames;
+  int32_t background;
+  float alpha, beta, gamma, T;
+} b2_shoot_args;
+
+int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps);
+int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Adjoint of b2_shoot_fwd through expmap and flat: given gu = dL/du^S (NULL = 0),
+ * gvel = dL/dvel, gm0 = dL/dm0 (explicit dependence, e.g. sum(v*m); NULL = 0),
+ * returns gv0 = dL/dv0 (P,2,H,W).  Needs traj from the forward. */
+int64_t b2_shoot_bwd_workspace_bytes(int64_t P, int64_t H, int64_t W);
+int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0, const float* m0,
+                 const float* traj, float* gv0, int64_t P, int64_t H, int64_t W,
+                 int num_steps, float alpha, float beta, float gamma, float T, int background,
+                 int v0_is_momentum /* != 0: return dL/dm0 instead of dL/dv0 */,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Device properties the host side needs for grid sizing / reporting. */
+int b2_device_sm_count(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2LDDMM_H */

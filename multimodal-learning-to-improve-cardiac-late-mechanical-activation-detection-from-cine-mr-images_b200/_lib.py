@@ -1,0 +1,135 @@
+"""ctypes binding of the C-ABI library ``libb2lddmm.so`` (include/b2lddmm.h).
+
+The library is the product path.  There is NO CPU fallback: if the shared
+library is missing, or an op is handed a non-CUDA tensor, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+import torch
+
+_LIB_PATH = pathlib.Path(__file__).resolve().parent / "libb2lddmm.so"
+_lib = None
+
+c_f = C.c_void_p       # float* / any device pointer
+c_i64 = C.c_int64
+c_int = C.c_int
+c_float = C.c_float
+
+
+class ShootArgs(C.Structure):
+    """Mirror of ``b2_shoot_args`` (include/b2lddmm.h)."""
+    _fields_ = [
+        ("v0", C.c_void_p), ("src", C.c_void_p), ("tar", C.c_void_p),
+        ("moments", C.c_void_p), ("table", C.c_void_p),
+        ("m0", C.c_void_p), ("vel", C.c_void_p), ("u", C.c_void_p), ("sdef", C.c_void_p),
+        ("S", C.c_void_p), ("counts", C.c_void_p), ("traj", C.c_void_p),
+        ("B", C.c_int64), ("T1", C.c_int64), ("H", C.c_int64), ("W", C.c_int64),
+        ("num_steps", C.c_int32), ("src_per_pair", C.c_int32), ("v0_is_momentum", C.c_int32),
+        ("n_sectors", C.c_int32), ("n_frames", C.c_int32), ("background", C.c_int32),
+        ("alpha", C.c_float), ("beta", C.c_float), ("gamma", C.c_float), ("T", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
+SIGNATURES = {
+    "b2_version": (c_int, []),
+    "b2_error_string": (C.c_char_p, [c_int]),
+    "b2_interp_fwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_interp_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_warp_fwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_warp_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_splat_fwd": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_compose_fwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_compose_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_float, c_int, c_f]),
+    "b2_jtv_fwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_int, c_f]),
+    "b2_jtv_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_int, c_f]),
+    "b2_adstar_fwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_f]),
+    "b2_adstar_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_f]),
+    "b2_fluid_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "b2_fluid_apply": (c_int, [c_f, c_f, c_i64, c_i64, c_i64, c_float, c_float, c_float, c_int, c_f, c_i64, c_f]),
+    "b2_sector_table_host": (c_int, [c_int, C.POINTER(C.c_int32)]),
+    "b2_mask_moments": (c_int, [c_f, c_f, c_i64, c_i64, c_i64, c_f]),
+    "b2_sector_map_i32": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_f]),
+    "b2_strain_sector_fwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_f]),
+    "b2_strain_sector_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_f]),
+    "b2_shoot_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_int]),
+    "b2_shoot_fwd": (c_int, [C.POINTER(ShootArgs), c_f, c_i64, c_f]),
+    "b2_shoot_bwd_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "b2_shoot_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_float, c_float, c_float,
+                             c_float, c_int, c_int, c_f, c_i64, c_f]),
+    "b2_device_sm_count": (c_int, [c_int]),
+}
+
+
+def lib_path() -> pathlib.Path:
+    return _LIB_PATH
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raise loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"CUDA extension {_LIB_PATH} is missing - build it with "
+                "`python __graft_entry__.py` (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().b2_error_string(int(code)).decode()
+        raise B2Error(f"{what or 'b2lddmm'} failed with code {code}: {msg}")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors, dtype=torch.float32):
+    """All tensors must be contiguous CUDA tensors of one device (no CPU fallback)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise B2Error("b2lddmm ops run on CUDA tensors only (there is no CPU fallback)")
+        if dtype is not None and t.dtype != dtype:
+            raise B2Error(f"expected dtype {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise B2Error("expected a contiguous tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise B2Error("all tensors must live on the same device")
+    return dev
+
+
+_launches = 0
+
+
+def count_launch(n: int = 1) -> None:
+    """Bookkeeping for bench.py's ``gpu_launches``: kernels of OUR library launched."""
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches

@@ -1,0 +1,154 @@
+// Shared device helpers for the registration-to-strain kernels (sm_100a).
+// Math follows SURVEY.md Appendix A; the CPU oracle restates the same formulas
+// in oracle/lddmm.py and oracle/strain.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2lddmm.h"
+
+#define B2_CHECK_LAUNCH()                         \
+  do {                                            \
+    cudaError_t e__ = cudaGetLastError();         \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+#define B2_CUDA(call)                             \
+  do {                                            \
+    cudaError_t e__ = (call);                     \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+namespace b2 {
+
+constexpr int kMaxGridY = 65535;
+
+__host__ __device__ inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// ---------------------------------------------------------------------------
+// Bilinear taps (A.1).  Indices are background-ruled independently; weights are
+// never renormalised.  v00=(i,j) v10=(i+1,j) v01=(i,j+1) v11=(i+1,j+1).
+// ---------------------------------------------------------------------------
+struct Taps {
+  int o00, o10, o01, o11;   // flat offsets i*W + j after the background rule
+  float a, b;               // fractional parts along rows / cols
+  float m00, m10, m01, m11; // 1 = tap contributes, 0 = outside under the zero rule
+};
+
+template <int BG>
+__device__ __forceinline__ Taps make_taps(float p0, float p1, int H, int W) {
+  Taps t;
+  float f0 = floorf(p0), f1 = floorf(p1);
+  t.a = p0 - f0;
+  t.b = p1 - f1;
+  int i0 = (int)fminf(fmaxf(f0, -2.0f), (float)(H + 1));
+  int j0 = (int)fminf(fmaxf(f1, -2.0f), (float)(W + 1));
+  int i1 = i0 + 1, j1 = j0 + 1;
+  if (BG == B2_BG_ZERO) {
+    float ri0 = (i0 >= 0 && i0 < H) ? 1.f : 0.f, ri1 = (i1 >= 0 && i1 < H) ? 1.f : 0.f;
+    float cj0 = (j0 >= 0 && j0 < W) ? 1.f : 0.f, cj1 = (j1 >= 0 && j1 < W) ? 1.f : 0.f;
+    t.m00 = ri0 * cj0; t.m10 = ri1 * cj0; t.m01 = ri0 * cj1; t.m11 = ri1 * cj1;
+  } else {
+    t.m00 = t.m10 = t.m01 = t.m11 = 1.f;
+  }
+  i0 = min(max(i0, 0), H - 1); i1 = min(max(i1, 0), H - 1);
+  j0 = min(max(j0, 0), W - 1); j1 = min(max(j1, 0), W - 1);
+  t.o00 = i0 * W + j0; t.o10 = i1 * W + j0; t.o01 = i0 * W + j1; t.o11 = i1 * W + j1;
+  return t;
+}
+
+template <int BG>
+__device__ __forceinline__ float tap_sample(const Taps& t, float v00, float v10, float v01, float v11) {
+  float oma = 1.f - t.a, omb = 1.f - t.b;
+  if (BG == B2_BG_ZERO) { v00 *= t.m00; v10 *= t.m10; v01 *= t.m01; v11 *= t.m11; }
+  // same association as the oracle: sum of (wi*wj)*v in tap order 00, 01, 10, 11
+  return (((oma * omb) * v00 + (oma * t.b) * v01) + (t.a * omb) * v10) + (t.a * t.b) * v11;
+}
+
+// d(sample)/d(p0), d(sample)/d(p1)
+template <int BG>
+__device__ __forceinline__ void tap_grad(const Taps& t, float v00, float v10, float v01, float v11,
+                                         float& g0, float& g1) {
+  if (BG == B2_BG_ZERO) { v00 *= t.m00; v10 *= t.m10; v01 *= t.m01; v11 *= t.m11; }
+  g0 = (1.f - t.b) * (v10 - v00) + t.b * (v11 - v01);
+  g1 = (1.f - t.a) * (v01 - v00) + t.a * (v11 - v10);
+}
+
+// ---------------------------------------------------------------------------
+// Finite differences (A.3): central inside, one-sided at the first/last index.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void diff_idx(int k, int n, int& lo, int& hi, float& s) {
+  lo = max(k - 1, 0);
+  hi = min(k + 1, n - 1);
+  s = (k == 0 || k == n - 1) ? 1.f : 0.5f;
+}
+
+// Transposed difference operator, gathered form:
+// (D^T q)[k] = [k>=1] s(k-1) q[k-1] + [k==n-1] q[k] - [k<=n-2] s(k+1) q[k+1] - [k==0] q[k]
+__device__ __forceinline__ float diff_scale(int j, int n) { return (j == 0 || j == n - 1) ? 1.f : 0.5f; }
+__device__ __forceinline__ float diffT(float qm, float q0, float qp, int k, int n) {
+  float v = 0.f;
+  if (k >= 1) v += diff_scale(k - 1, n) * qm;
+  if (k == n - 1) v += q0;
+  if (k <= n - 2) v -= diff_scale(k + 1, n) * qp;
+  if (k == 0) v -= q0;
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Sector classification (D7) - integer predicates only.
+// table[2k] = round(2^20 sin(2 pi k/n)), table[2k+1] = round(2^20 cos(2 pi k/n)).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int classify_sector(long long dr, long long dc, const int32_t* __restrict__ table, int n) {
+  if (dr == 0 && dc == 0) return -1;
+  float th = atan2f((float)dr, (float)dc);
+  if (th < 0.f) th += 6.283185307179586f;
+  int k = (int)floorf(th * ((float)n * 0.15915494309189535f));
+  k = min(max(k, 0), n - 1);
+  for (int it = 0; it < n; ++it) {
+    int k1 = (k + 1 == n) ? 0 : k + 1;
+    long long lo = (long long)table[2 * k + 1] * dr - (long long)table[2 * k] * dc;
+    long long hi = (long long)table[2 * k1 + 1] * dr - (long long)table[2 * k1] * dc;
+    if (lo < 0) k = (k == 0) ? n - 1 : k - 1;
+    else if (hi >= 0) k = k1;
+    else break;
+  }
+  return k;
+}
+
+// Centroid as float: double division then cast; image centre for an empty mask.
+__device__ __forceinline__ void centroid_from_moments(const long long* mom, int H, int W, float& c0, float& c1) {
+  long long cnt = mom[0];
+  if (cnt > 0) {
+    c0 = (float)((double)mom[1] / (double)cnt);
+    c1 = (float)((double)mom[2] / (double)cnt);
+  } else {
+    c0 = (float)((H - 1) * 0.5);
+    c1 = (float)((W - 1) * 0.5);
+  }
+}
+
+constexpr float kDetEps = 1e-6f;
+constexpr float kRad2Eps = 1e-12f;
+
+// Circumferential Green-Lagrange strain at one pixel (A.7).  Returns false when skipped.
+struct EccTerms {
+  float G00, G01, G10, G11, det, n0, n1, rad2, t0, t1, den, q;
+};
+__device__ __forceinline__ bool ecc_eval(float d00, float d01, float d10, float d11,
+                                         float X0, float X1, float c0, float c1, EccTerms& e, float& ecc) {
+  e.G00 = 1.f + d00; e.G01 = d01; e.G10 = d10; e.G11 = 1.f + d11;
+  e.det = e.G00 * e.G11 - e.G01 * e.G10;
+  e.n0 = X0 - c0; e.n1 = X1 - c1;
+  e.rad2 = e.n0 * e.n0 + e.n1 * e.n1;
+  float e0 = -e.n1, e1 = e.n0;
+  e.t0 = e.G11 * e0 - e.G01 * e1;
+  e.t1 = e.G00 * e1 - e.G10 * e0;
+  bool valid = (e.rad2 >= kRad2Eps) && (fabsf(e.det) >= kDetEps);
+  e.den = valid ? e.rad2 * e.det * e.det : 1.f;
+  e.q = (e.t0 * e.t0 + e.t1 * e.t1) / e.den;
+  ecc = valid ? 0.5f * (e.q - 1.f) : 0.f;
+  return valid;
+}
+
+}  // namespace b2

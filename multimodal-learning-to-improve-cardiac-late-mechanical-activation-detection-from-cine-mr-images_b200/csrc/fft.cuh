@@ -1,0 +1,253 @@
+// Batched shared-memory FFT + Fourier-domain fluid-metric multiplier (sm_100a).
+// Replaces torch.rfft/irfft (cuFFT) + lagomorph_ext.fluid_operator.
+//
+// The two real components of a vector field are packed as ONE complex field
+// z = f0 + i*f1, so a single complex 2-D FFT carries both spectra:
+//   F0(k) = (Z(k) + conj Z(-k))/2,  F1(k) = (Z(k) - conj Z(-k))/(2i).
+// Applying the real symmetric 2x2 symbol [[a,b],[b,d]](k) (even in k) and
+// re-packing gives   W(k) = A Z(k) + B conj Z(-k),  A = (a+d)/2, B = (a-d)/2 + i b,
+// so the multiplier couples storage cell k with its mirror -k and nothing else.
+//
+// Each 1-D FFT of length N = N1*N2 runs as two in-register DFT passes (radix
+// N1 then N2, both in {4,8,16}) that are IN PLACE per thread; the forward
+// transform leaves the spectrum in a digit-permuted order (cell N2*k1+k2 holds
+// frequency k1+N1*k2) which the multiplier decodes and the inverse consumes, so
+// no reordering pass exists.  One routine serves rows and columns: lanes run
+// across "lines" and each thread's points are strided; with the odd row pitch
+// W+1 (in float2) both directions are shared-memory bank-conflict free.
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// x * (c + i*s)
+__device__ __forceinline__ float2 cmul(float2 x, float c, float s) {
+  return make_float2(x.x * c - x.y * s, x.x * s + x.y * c);
+}
+
+// x * exp(DIR * 2*pi*i * t/16), t compile-time after unrolling
+template <int DIR>
+__device__ __forceinline__ float2 tw16(float2 x, int t) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+  switch (t & 15) {
+    case 0: return x;
+    case 4: return DIR > 0 ? make_float2(-x.y, x.x) : make_float2(x.y, -x.x);
+    case 8: return make_float2(-x.x, -x.y);
+    case 12: return DIR > 0 ? make_float2(x.y, -x.x) : make_float2(-x.y, x.x);
+    case 1: return cmul(x, C1, DIR * S1);
+    case 2: return cmul(x, R2, DIR * R2);
+    case 3: return cmul(x, S1, DIR * C1);
+    case 5: return cmul(x, -S1, DIR * C1);
+    case 6: return cmul(x, -R2, DIR * R2);
+    case 7: return cmul(x, -C1, DIR * S1);
+    default: return cmul(x, 1.f, 0.f);  // t in 9..15 never generated (k < R/2)
+  }
+}
+
+// In-register DFT of R points, natural order in and out (radix-2 DIT recursion,
+// fully unrolled; twiddles are compile-time constants).
+template <int R, int DIR>
+struct DftReg {
+  static __device__ __forceinline__ void run(float2 (&x)[R]) {
+    float2 e[R / 2], o[R / 2];
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
+    DftReg<R / 2, DIR>::run(e);
+    DftReg<R / 2, DIR>::run(o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      const float2 t = tw16<DIR>(o[k], k * (16 / R));
+      x[k] = cadd(e[k], t);
+      x[k + R / 2] = csub(e[k], t);
+    }
+  }
+};
+template <int DIR>
+struct DftReg<1, DIR> {
+  static __device__ __forceinline__ void run(float2 (&)[1]) {}
+};
+
+template <int N> struct Fact;
+template <> struct Fact<16>  { static constexpr int N1 = 4,  N2 = 4;  };
+template <> struct Fact<32>  { static constexpr int N1 = 8,  N2 = 4;  };
+template <> struct Fact<64>  { static constexpr int N1 = 8,  N2 = 8;  };
+template <> struct Fact<128> { static constexpr int N1 = 16, N2 = 8;  };
+template <> struct Fact<256> { static constexpr int N1 = 16, N2 = 16; };
+
+// storage cell <-> frequency of the digit-permuted spectrum
+template <int N> __device__ __forceinline__ int cell_to_freq(int p) {
+  return (p / Fact<N>::N2) + Fact<N>::N1 * (p % Fact<N>::N2);
+}
+template <int N> __device__ __forceinline__ int freq_to_cell(int k) {
+  return Fact<N>::N2 * (k % Fact<N>::N1) + (k / Fact<N>::N1);
+}
+
+// tw[j] = (cos(2 pi j/N), sin(2 pi j/N)), j in [0, N)
+template <int N>
+__device__ __forceinline__ void init_twiddles(float2* tw, int tid, int nthreads) {
+  for (int j = tid; j < N; j += nthreads) {
+    float s, c;
+    sincospif(2.0f * (float)j / (float)N, &s, &c);
+    tw[j] = make_float2(c, s);
+  }
+}
+
+// FFTs of length N along element stride `es`, for NL lines spaced `ls` apart.
+// Forward (DIR=-1): natural in -> permuted out.  Inverse (DIR=+1): permuted in ->
+// natural out, unnormalised.  Ends with __syncthreads().
+template <int N, int NL, int DIR, int NT>
+__device__ __forceinline__ void fft_lines(float2* __restrict__ z, int es, int ls,
+                                          const float2* __restrict__ tw, int tid) {
+  constexpr int N1 = Fact<N>::N1, N2 = Fact<N>::N2;
+  if (DIR < 0) {
+    for (int t = tid; t < NL * N2; t += NT) {
+      const int line = t % NL, n2 = t / NL;
+      float2* base = z + line * ls + n2 * es;
+      float2 x[N1];
+#pragma unroll
+      for (int n1 = 0; n1 < N1; ++n1) x[n1] = base[(N2 * n1) * es];
+      DftReg<N1, -1>::run(x);
+#pragma unroll
+      for (int k1 = 1; k1 < N1; ++k1) {
+        const float2 w = tw[n2 * k1];
+        x[k1] = cmul(x[k1], w.x, -w.y);
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < N1; ++k1) base[(N2 * k1) * es] = x[k1];
+    }
+    __syncthreads();
+    for (int t = tid; t < NL * N1; t += NT) {
+      const int line = t % NL, k1 = t / NL;
+      float2* base = z + line * ls + (N2 * k1) * es;
+      float2 y[N2];
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) y[n2] = base[n2 * es];
+      DftReg<N2, -1>::run(y);
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) base[k2 * es] = y[k2];
+    }
+    __syncthreads();
+  } else {
+    for (int t = tid; t < NL * N1; t += NT) {
+      const int line = t % NL, k1 = t / NL;
+      float2* base = z + line * ls + (N2 * k1) * es;
+      float2 y[N2];
+#pragma unroll
+      for (int k2 = 0; k2 < N2; ++k2) y[k2] = base[k2 * es];
+      DftReg<N2, +1>::run(y);
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) {
+        const float2 w = tw[n2 * k1];
+        base[n2 * es] = (n2 == 0) ? y[n2] : cmul(y[n2], w.x, w.y);
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < NL * N2; t += NT) {
+      const int line = t % NL, n2 = t / NL;
+      float2* base = z + line * ls + n2 * es;
+      float2 x[N1];
+#pragma unroll
+      for (int k1 = 0; k1 < N1; ++k1) x[k1] = base[(N2 * k1) * es];
+      DftReg<N1, +1>::run(x);
+#pragma unroll
+      for (int n1 = 0; n1 < N1; ++n1) base[(N2 * n1) * es] = x[n1];
+    }
+    __syncthreads();
+  }
+}
+
+// Per-axis symbol LUTs: cs[k] = (4 sin^2(pi k/N), sin(2 pi k/N)) = (2(1-cos), sin)
+template <int N>
+__device__ __forceinline__ void init_symbol_lut(float2* cs, int tid, int nthreads) {
+  for (int k = tid; k < N; k += nthreads) {
+    float s, c, sh, ch;
+    sincospif(2.0f * (float)k / (float)N, &s, &c);
+    sincospif((float)k / (float)N, &sh, &ch);
+    cs[k] = make_float2(4.0f * sh * sh, s);
+  }
+}
+
+struct FluidParams { float alpha, beta, gamma, scale; };
+
+// A, B of W = A Z + B conj(Z~) at frequency (k0, k1)
+template <bool INVERSE>
+__device__ __forceinline__ void fluid_coeffs(const FluidParams& fp, float2 cs0, float2 cs1,
+                                             float& A, float& Br, float& Bi) {
+  const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
+  const float L00 = lam + fp.beta * cs0.x;
+  const float L11 = lam + fp.beta * cs1.x;
+  const float L01 = fp.beta * (cs0.y * cs1.y);
+  float a, d, b;
+  if (INVERSE) {
+    const float idet = 1.0f / (L00 * L11 - L01 * L01);
+    a = L11 * idet; d = L00 * idet; b = -L01 * idet;
+  } else {
+    a = L00; d = L11; b = L01;
+  }
+  A = fp.scale * 0.5f * (a + d);
+  Br = fp.scale * 0.5f * (a - d);
+  Bi = fp.scale * b;
+}
+
+// In-place multiplier on the permuted 2-D spectrum z[r*LD + c]; each thread owns a
+// cell and its mirror (-k0, -k1) and writes both.  Ends with __syncthreads().
+template <int H, int W, bool INVERSE, int NT>
+__device__ __forceinline__ void fluid_multiply(float2* __restrict__ z, int LD, const float2* __restrict__ csH,
+                                               const float2* __restrict__ csW, const FluidParams fp, int tid) {
+  for (int t = tid; t < H * W; t += NT) {
+    const int pr = t / W, pc = t % W;
+    const int k0 = cell_to_freq<H>(pr), k1 = cell_to_freq<W>(pc);
+    const int qr = freq_to_cell<H>((H - k0) & (H - 1)), qc = freq_to_cell<W>((W - k1) & (W - 1));
+    const int lin = pr * W + pc, linq = qr * W + qc;
+    if (lin > linq) continue;
+    float A, Br, Bi;
+    fluid_coeffs<INVERSE>(fp, csH[k0], csW[k1], A, Br, Bi);
+    const float2 Z = z[pr * LD + pc];
+    const float2 Zq = z[qr * LD + qc];
+    // W(k) = A Z + B conj(Zq);  W(-k) = A Zq + B conj(Z)
+    z[pr * LD + pc] = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
+    if (lin != linq)
+      z[qr * LD + qc] = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
+  }
+  __syncthreads();
+}
+
+// Whole operator on a field resident in shared memory as z = f0 + i f1.
+template <int H, int W, bool INVERSE, int NT>
+__device__ __forceinline__ void fluid_smem(float2* z, const float2* twH, const float2* twW,
+                                           const float2* csH, const float2* csW, const FluidParams fp, int tid) {
+  constexpr int LD = W + 1;
+  fft_lines<W, H, -1, NT>(z, 1, LD, twW, tid);      // rows: FFT along c, lanes along r
+  fft_lines<H, W, -1, NT>(z, LD, 1, twH, tid);      // cols: FFT along r, lanes along c
+  fluid_multiply<H, W, INVERSE, NT>(z, LD, csH, csW, fp, tid);
+  fft_lines<H, W, +1, NT>(z, LD, 1, twH, tid);
+  fft_lines<W, H, +1, NT>(z, 1, LD, twW, tid);
+}
+
+template <int H, int W>
+struct FluidSmem {
+  static constexpr int LD = W + 1;
+  static constexpr size_t z_bytes = sizeof(float2) * (size_t)H * LD;
+  static constexpr size_t lut_bytes = sizeof(float2) * 2 * (size_t)(H + W);
+  static constexpr size_t bytes = z_bytes + lut_bytes;
+  // layout: z | twH[H] | twW[W] | csH[H] | csW[W]
+  static __device__ __forceinline__ void carve(unsigned char* smem, float2*& z, float2*& twH, float2*& twW,
+                                               float2*& csH, float2*& csW) {
+    z = reinterpret_cast<float2*>(smem);
+    twH = z + (size_t)H * LD;
+    twW = twH + H;
+    csH = twW + W;
+    csW = csH + H;
+  }
+  static __device__ __forceinline__ void init_luts(float2* twH, float2* twW, float2* csH, float2* csW,
+                                                   int tid, int nthreads) {
+    init_twiddles<H>(twH, tid, nthreads);
+    init_twiddles<W>(twW, tid, nthreads);
+    init_symbol_lut<H>(csH, tid, nthreads);
+    init_symbol_lut<W>(csW, tid, nthreads);
+  }
+};
+
+}  // namespace b2

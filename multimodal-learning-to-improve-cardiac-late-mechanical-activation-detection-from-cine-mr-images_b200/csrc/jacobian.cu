@@ -1,0 +1,268 @@
+// lagomorph.jacobian_times_vectorfield and lagomorph.Ad_star - forward and adjoint.
+// Replaces lagomorph_ext.jacobian_times_vectorfield_forward/backward.
+//
+// Ad_star is ONE kernel: the 4-tap gather of m0 at x + u(x) and the (I + Du)^T
+// 5-point stencil on u are fused, so the intermediate m0 o (id+u) never goes to
+// HBM (the reference path runs two kernels with a (P,2,H,W) temporary).
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kThreadsJ = 256;
+
+struct Jac { float d00, d01, d10, d11; };   // d_ab = d v_a / d x_b
+
+__device__ __forceinline__ Jac jac_at(const float* __restrict__ v0, const float* __restrict__ v1,
+                                      int r, int c, int H, int W) {
+  int rlo, rhi, clo, chi; float sr, sc;
+  diff_idx(r, H, rlo, rhi, sr);
+  diff_idx(c, W, clo, chi, sc);
+  Jac J;
+  J.d00 = sr * (v0[rhi * W + c] - v0[rlo * W + c]);
+  J.d10 = sr * (v1[rhi * W + c] - v1[rlo * W + c]);
+  J.d01 = sc * (v0[r * W + chi] - v0[r * W + clo]);
+  J.d11 = sc * (v1[r * W + chi] - v1[r * W + clo]);
+  return J;
+}
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(kThreadsJ)
+jtv_fwd_kernel(const float* __restrict__ v, const float* __restrict__ w, float* __restrict__ out,
+               int P, int H, int W, float disp) {
+  const int N = H * W;
+  const int x = blockIdx.x * kThreadsJ + threadIdx.x;
+  if (x >= N) return;
+  const int r = x / W, c = x - r * W;
+  for (int p = blockIdx.y; p < P; p += gridDim.y) {
+    const float* vp = v + (size_t)p * 2 * N;
+    const float* wp = w + (size_t)p * 2 * N;
+    const Jac J = jac_at(vp, vp + N, r, c, H, W);
+    const float w0 = wp[x], w1 = wp[N + x];
+    float o0, o1;
+    if (TRANSPOSE) { o0 = J.d00 * w0 + J.d10 * w1; o1 = J.d01 * w0 + J.d11 * w1; }
+    else           { o0 = J.d00 * w0 + J.d01 * w1; o1 = J.d10 * w0 + J.d11 * w1; }
+    float* op = out + (size_t)p * 2 * N;
+    op[x] = o0 + disp * w0;
+    op[N + x] = o1 + disp * w1;
+  }
+}
+
+// gather the transposed-difference of the products q_ab = g_a * w_b around (r,c)
+__device__ __forceinline__ void load5(const float* __restrict__ f, int r, int c, int H, int W,
+                                      float& up, float& dn, float& lf, float& rt, float& ce) {
+  ce = f[r * W + c];
+  up = f[max(r - 1, 0) * W + c];
+  dn = f[min(r + 1, H - 1) * W + c];
+  lf = f[r * W + max(c - 1, 0)];
+  rt = f[r * W + min(c + 1, W - 1)];
+}
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(kThreadsJ)
+jtv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ w,
+               float* __restrict__ dv, float* __restrict__ dw, int P, int H, int W, float disp) {
+  const int N = H * W;
+  const int x = blockIdx.x * kThreadsJ + threadIdx.x;
+  if (x >= N) return;
+  const int r = x / W, c = x - r * W;
+  for (int p = blockIdx.y; p < P; p += gridDim.y) {
+    const float* vp = v + (size_t)p * 2 * N;
+    const float* wp = w + (size_t)p * 2 * N;
+    const float* gp = g + (size_t)p * 2 * N;
+    if (dw) {
+      const Jac J = jac_at(vp, vp + N, r, c, H, W);
+      const float g0 = gp[x], g1 = gp[N + x];
+      float o0, o1;  // M^T g
+      if (TRANSPOSE) { o0 = J.d00 * g0 + J.d01 * g1; o1 = J.d10 * g0 + J.d11 * g1; }
+      else           { o0 = J.d00 * g0 + J.d10 * g1; o1 = J.d01 * g0 + J.d11 * g1; }
+      float* dp = dw + (size_t)p * 2 * N;
+      dp[x] = o0 + disp * g0;
+      dp[N + x] = o1 + disp * g1;
+    }
+    if (dv) {
+      float g0u, g0d, g0l, g0r, g0c, g1u, g1d, g1l, g1r, g1c;
+      float w0u, w0d, w0l, w0r, w0c, w1u, w1d, w1l, w1r, w1c;
+      load5(gp, r, c, H, W, g0u, g0d, g0l, g0r, g0c);
+      load5(gp + N, r, c, H, W, g1u, g1d, g1l, g1r, g1c);
+      load5(wp, r, c, H, W, w0u, w0d, w0l, w0r, w0c);
+      load5(wp + N, r, c, H, W, w1u, w1d, w1l, w1r, w1c);
+      float o0, o1;
+      if (TRANSPOSE) {
+        // out_a = sum_b (d_a v_b) w_b  ->  dv_b = sum_a D_a^T (g_a w_b)
+        o0 = diffT(g0u * w0u, g0c * w0c, g0d * w0d, r, H) + diffT(g1l * w0l, g1c * w0c, g1r * w0r, c, W);
+        o1 = diffT(g0u * w1u, g0c * w1c, g0d * w1d, r, H) + diffT(g1l * w1l, g1c * w1c, g1r * w1r, c, W);
+      } else {
+        // out_a = sum_b (d_b v_a) w_b  ->  dv_a = sum_b D_b^T (g_a w_b)
+        o0 = diffT(g0u * w0u, g0c * w0c, g0d * w0d, r, H) + diffT(g0l * w1l, g0c * w1c, g0r * w1r, c, W);
+        o1 = diffT(g1u * w0u, g1c * w0c, g1d * w0d, r, H) + diffT(g1l * w1l, g1c * w1c, g1r * w1r, c, W);
+      }
+      float* dp = dv + (size_t)p * 2 * N;
+      dp[x] = o0;
+      dp[N + x] = o1;
+    }
+  }
+}
+
+// m = (I + Du)^T (m0 o (id + u))
+template <int BG>
+__global__ void __launch_bounds__(kThreadsJ)
+adstar_fwd_kernel(const float* __restrict__ u, const float* __restrict__ m0, float* __restrict__ out,
+                  int P, int H, int W) {
+  const int N = H * W;
+  const int x = blockIdx.x * kThreadsJ + threadIdx.x;
+  if (x >= N) return;
+  const int r = x / W, c = x - r * W;
+  for (int p = blockIdx.y; p < P; p += gridDim.y) {
+    const float* up = u + (size_t)p * 2 * N;
+    const float* mp = m0 + (size_t)p * 2 * N;
+    const Jac J = jac_at(up, up + N, r, c, H, W);
+    const Taps t = make_taps<BG>((float)r + up[x], (float)c + up[N + x], H, W);
+    const float w0 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
+    const float w1 = tap_sample<BG>(t, mp[N + t.o00], mp[N + t.o10], mp[N + t.o01], mp[N + t.o11]);
+    float* op = out + (size_t)p * 2 * N;
+    op[x] = w0 + (J.d00 * w0 + J.d10 * w1);
+    op[N + x] = w1 + (J.d01 * w0 + J.d11 * w1);
+  }
+}
+
+// Adjoint of adstar_fwd given wbuf = m0 o (id+u).
+template <int BG, bool NEED_DU, bool NEED_DM>
+__global__ void __launch_bounds__(kThreadsJ)
+adstar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ m0,
+                  const float* __restrict__ wbuf, float* __restrict__ du, float* __restrict__ dm0,
+                  int P, int H, int W) {
+  const int N = H * W;
+  const int x = blockIdx.x * kThreadsJ + threadIdx.x;
+  if (x >= N) return;
+  const int r = x / W, c = x - r * W;
+  for (int p = blockIdx.y; p < P; p += gridDim.y) {
+    const float* up = u + (size_t)p * 2 * N;
+    const float* mp = m0 + (size_t)p * 2 * N;
+    const float* gp = g + (size_t)p * 2 * N;
+    const float* wp = wbuf + (size_t)p * 2 * N;
+    const Jac J = jac_at(up, up + N, r, c, H, W);
+    const float g0 = gp[x], g1 = gp[N + x];
+    // gw = (I + Du) g
+    const float gw0 = g0 + (J.d00 * g0 + J.d01 * g1);
+    const float gw1 = g1 + (J.d10 * g0 + J.d11 * g1);
+    const Taps t = make_taps<BG>((float)r + up[x], (float)c + up[N + x], H, W);
+    if (NEED_DM) {
+      const float oma = 1.f - t.a, omb = 1.f - t.b;
+      float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
+      if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
+      float* d = dm0 + (size_t)p * 2 * N;
+      atomicAdd(d + t.o00, w00 * gw0); atomicAdd(d + t.o01, w01 * gw0);
+      atomicAdd(d + t.o10, w10 * gw0); atomicAdd(d + t.o11, w11 * gw0);
+      d += N;
+      atomicAdd(d + t.o00, w00 * gw1); atomicAdd(d + t.o01, w01 * gw1);
+      atomicAdd(d + t.o10, w10 * gw1); atomicAdd(d + t.o11, w11 * gw1);
+    }
+    if (NEED_DU) {
+      float a0, a1, b0, b1;
+      tap_grad<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11], a0, a1);
+      tap_grad<BG>(t, mp[N + t.o00], mp[N + t.o10], mp[N + t.o01], mp[N + t.o11], b0, b1);
+      float o0 = gw0 * a0 + gw1 * b0;
+      float o1 = gw0 * a1 + gw1 * b1;
+      // Jacobian part: m_a = ... + sum_b (d_a u_b) w_b  ->  du_b += sum_a D_a^T (g_a w_b)
+      float g0u, g0d, g0l, g0r, g0c, g1u, g1d, g1l, g1r, g1c;
+      float w0u, w0d, w0l, w0r, w0c, w1u, w1d, w1l, w1r, w1c;
+      load5(gp, r, c, H, W, g0u, g0d, g0l, g0r, g0c);
+      load5(gp + N, r, c, H, W, g1u, g1d, g1l, g1r, g1c);
+      load5(wp, r, c, H, W, w0u, w0d, w0l, w0r, w0c);
+      load5(wp + N, r, c, H, W, w1u, w1d, w1l, w1r, w1c);
+      o0 += diffT(g0u * w0u, g0c * w0c, g0d * w0d, r, H) + diffT(g1l * w0l, g1c * w0c, g1r * w0r, c, W);
+      o1 += diffT(g0u * w1u, g0c * w1c, g0d * w1d, r, H) + diffT(g1l * w1l, g1c * w1c, g1r * w1r, c, W);
+      float* dp = du + (size_t)p * 2 * N;
+      dp[x] = o0;
+      dp[N + x] = o1;
+    }
+  }
+}
+
+static int check_pf(int64_t P, int64_t H, int64_t W) {
+  if (P <= 0 || H < 2 || W < 2) return B2_E_SHAPE;
+  if (H * W > (int64_t)1 << 30 || P > (int64_t)1 << 30) return B2_E_SHAPE;
+  return B2_OK;
+}
+static dim3 pgrid(int64_t P, int64_t N) {
+  return dim3((unsigned)((N + kThreadsJ - 1) / kThreadsJ), (unsigned)(P < kMaxGridY ? P : kMaxGridY), 1);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_jtv_fwd(const float* v, const float* w, float* out, int64_t P, int64_t H, int64_t W,
+                          int displacement, int transpose, void* stream) {
+  if (!v || !w || !out) return B2_E_NULL;
+  if (int e = check_pf(P, H, W)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float disp = displacement ? 1.f : 0.f;
+  if (transpose) jtv_fwd_kernel<true><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(v, w, out, (int)P, (int)H, (int)W, disp);
+  else jtv_fwd_kernel<false><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(v, w, out, (int)P, (int)H, (int)W, disp);
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+extern "C" int b2_jtv_bwd(const float* gout, const float* v, const float* w, float* dv, float* dw,
+                          int64_t P, int64_t H, int64_t W, int displacement, int transpose, void* stream) {
+  if (!gout || !v || !w) return B2_E_NULL;
+  if (!dv && !dw) return B2_OK;
+  if (int e = check_pf(P, H, W)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float disp = displacement ? 1.f : 0.f;
+  if (transpose) jtv_bwd_kernel<true><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(gout, v, w, dv, dw, (int)P, (int)H, (int)W, disp);
+  else jtv_bwd_kernel<false><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(gout, v, w, dv, dw, (int)P, (int)H, (int)W, disp);
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+extern "C" int b2_adstar_fwd(const float* u, const float* m0, float* out, int64_t P, int64_t H, int64_t W,
+                             int background, void* stream) {
+  if (!u || !m0 || !out) return B2_E_NULL;
+  if (int e = check_pf(P, H, W)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (background == B2_BG_CLAMP)
+    adstar_fwd_kernel<B2_BG_CLAMP><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(u, m0, out, (int)P, (int)H, (int)W);
+  else if (background == B2_BG_ZERO)
+    adstar_fwd_kernel<B2_BG_ZERO><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(u, m0, out, (int)P, (int)H, (int)W);
+  else return B2_E_PARAM;
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+namespace b2 {
+int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* du, float* dm0, float* workspace,
+                    int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st) {
+  if (!gout || !u || !m0) return B2_E_NULL;
+  if (!du && !dm0) return B2_OK;
+  if (int e = check_pf(P, H, W)) return e;
+  if (background != B2_BG_CLAMP && background != B2_BG_ZERO) return B2_E_PARAM;
+  if (du && !workspace) return B2_E_WORKSPACE;
+  const int64_t N = H * W;
+  if (du) {
+    if (int e = b2_interp_fwd(m0, u, workspace, P, P, P, 2, H, W, 1.f, background, (void*)st)) return e;
+  }
+  if (dm0 && zero_dm0) B2_CUDA(cudaMemsetAsync(dm0, 0, sizeof(float) * (size_t)P * 2 * N, st));
+  dim3 grid = pgrid(P, N);
+#define B2_LAUNCH_AD(BGV, DU, DM) \
+  adstar_bwd_kernel<BGV, DU, DM><<<grid, kThreadsJ, 0, st>>>(gout, u, m0, workspace, du, dm0, (int)P, (int)H, (int)W)
+  if (background == B2_BG_CLAMP) {
+    if (du && dm0) B2_LAUNCH_AD(B2_BG_CLAMP, true, true);
+    else if (du) B2_LAUNCH_AD(B2_BG_CLAMP, true, false);
+    else B2_LAUNCH_AD(B2_BG_CLAMP, false, true);
+  } else {
+    if (du && dm0) B2_LAUNCH_AD(B2_BG_ZERO, true, true);
+    else if (du) B2_LAUNCH_AD(B2_BG_ZERO, true, false);
+    else B2_LAUNCH_AD(B2_BG_ZERO, false, true);
+  }
+#undef B2_LAUNCH_AD
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+}  // namespace b2
+
+extern "C" int b2_adstar_bwd(const float* gout, const float* u, const float* m0, float* du, float* dm0,
+                             float* workspace, int64_t P, int64_t H, int64_t W, int background, void* stream) {
+  return b2::adstar_bwd_impl(gout, u, m0, du, dm0, workspace, P, H, W, background, true, (cudaStream_t)stream);
+}

@@ -1,0 +1,420 @@
+// Fused geodesic shooting: flat + S x EPDiff_step + warp + strain/sector reduction.
+// Replaces the body of forward_volume (call site
+// /root/reference/modules/trainer/joint_registration_strainmat_LMA.py:307):
+//   m0 = metric.flat(v0); u = lm.expmap(metric, m0, num_steps=S); Sdef = lm.interp(src, u);
+//   strain_matrix = sector_reduce(strain(u), mask)            
+//
+// Path A (square grids up to 128x128): ONE persistent kernel, one CTA per
+// frame-pair at a time, grid = #SMs x resident CTAs.  The complex-packed working
+// field (m / v) lives in shared memory for the whole geodesic: every sharp() is
+// an in-SM FFT -> symbol multiply -> IFFT with no HBM round trip.  m0 and the
+// displacement u_s are written once per step to global memory and re-read by
+// the same CTA for the 4-tap gathers, so they are served from L1/L2 (the
+// working set of all resident CTAs is ~57 MB at 128^2, inside the 126 MB L2).
+// Compulsory HBM traffic per pair drops from the op-level 700*N bytes to the
+// inputs + outputs (~44*N bytes).
+//
+// Path B (256x256 / rectangular): the same algorithm as a sequence of the
+// op-level kernels (HBM-bound per op).
+#include "fft.cuh"
+#include "strain.cuh"
+
+namespace b2 {
+
+int fluid_apply_impl(const float* f, float* out, int64_t P, int64_t H, int64_t W, float alpha, float beta,
+                     float gamma, int inverse, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* du, float* dm0, float* workspace,
+                    int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st);
+
+constexpr int kFusedMaxSectors = 256;
+
+struct ShootParams {
+  b2_shoot_args a;
+  float* scratch;     // per-CTA: [u ping-pong | m0] fields
+  int64_t P;
+  int64_t field;      // 2*H*W floats
+};
+
+template <int H, int W>
+struct ShootSmem {
+  using FS = FluidSmem<H, W>;
+  static constexpr size_t bins_off = (FS::bytes + 15) & ~size_t(15);
+  static constexpr size_t bytes = bins_off + sizeof(int32_t) * 4 * kFusedMaxSectors;
+};
+
+template <int H, int W, int NT, int BG>
+__global__ void __launch_bounds__(NT)
+shoot_fwd_kernel(const ShootParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using FS = FluidSmem<H, W>;
+  constexpr int LD = FS::LD, N = H * W;
+  float2 *z, *twH, *twW, *csH, *csW;
+  FS::carve(smem_raw, z, twH, twW, csH, csW);
+  int32_t* tab_s = reinterpret_cast<int32_t*>(smem_raw + ShootSmem<H, W>::bins_off);
+  const b2_shoot_args& a = prm.a;
+  const int n_sectors = a.n_sectors;
+  float* sums_s = reinterpret_cast<float*>(tab_s + 2 * n_sectors);
+  int* cnts_s = tab_s + 3 * n_sectors;
+  const int tid = threadIdx.x;
+  const int S = a.num_steps;
+  const float dt = a.T / (float)S, mdt = -dt;
+  const FluidParams fp{a.alpha, a.beta, a.gamma, 1.0f / (float)N};
+  const int64_t P = prm.P;
+
+  FS::init_luts(twH, twW, csH, csW, tid, NT);
+  if (a.S)
+    for (int i = tid; i < 2 * n_sectors; i += NT) tab_s[i] = a.table[i];
+  float* scr_u = prm.scratch + (size_t)blockIdx.x * 2 * prm.field;
+  float* scr_m = scr_u + prm.field;
+  __syncthreads();
+
+  for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
+    const int64_t b = p / a.T1;
+    const int t = (int)(p % a.T1);
+    const float* m0g;
+    float* uout = a.u + (size_t)p * prm.field;
+
+    // ---- m0 = flat(v0)   (or m0 given directly: lagomorph.expmap(metric, m0))
+    {
+      const float* f0 = a.v0 + (size_t)p * prm.field;
+      for (int i = tid; i < N; i += NT) z[(i / W) * LD + (i % W)] = make_float2(__ldg(f0 + i), __ldg(f0 + N + i));
+    }
+    __syncthreads();
+    if (a.v0_is_momentum) {
+      m0g = a.v0 + (size_t)p * prm.field;
+    } else {
+      float* m0w = a.m0 ? a.m0 + (size_t)p * prm.field : scr_m;
+      fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
+      for (int i = tid; i < N; i += NT) {
+        const float2 v = z[(i / W) * LD + (i % W)];
+        m0w[i] = v.x;
+        m0w[N + i] = v.y;
+      }
+      m0g = m0w;
+      __syncthreads();   // every thread has read z before the next transform overwrites it
+    }
+
+    const float* ucur = nullptr;   // u_s (nullptr == identically zero)
+    for (int s = 0; s < S; ++s) {
+      // ---- m = Ad*_{u_s} m0  -> z
+      if (s > 0) {
+        __syncthreads();   // m0g / u_s stores visible; previous readers of z done
+        const float* u0 = ucur;
+        const float* u1 = ucur + N;
+        for (int i = tid; i < N; i += NT) {
+          const int r = i / W, c = i % W;
+          int rlo, rhi, clo, chi; float sr, sc;
+          diff_idx(r, H, rlo, rhi, sr);
+          diff_idx(c, W, clo, chi, sc);
+          const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
+          const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+          const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
+          const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+          const Taps tp = make_taps<BG>((float)r + u0[i], (float)c + u1[i], H, W);
+          const float w0 = tap_sample<BG>(tp, m0g[tp.o00], m0g[tp.o10], m0g[tp.o01], m0g[tp.o11]);
+          const float w1 = tap_sample<BG>(tp, m0g[N + tp.o00], m0g[N + tp.o10], m0g[N + tp.o01], m0g[N + tp.o11]);
+          z[r * LD + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+        }
+        __syncthreads();
+      }
+      // ---- v = sharp(m)  (in shared memory)
+      fluid_smem<H, W, true, NT>(z, twH, twW, csH, csW, fp, tid);
+
+      // ---- u_{s+1} = interp(u_s, v, -dt) - dt v ; trajectory / velocity outputs
+      float* unext;
+      if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * P + p) * prm.field : uout;
+      else unext = (((S - (s + 1)) & 1) == 0) ? uout : scr_u;
+      float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * P + p) * prm.field : nullptr;
+      float* utraj0 = (a.traj && s == 0) ? a.traj + ((size_t)p) * prm.field : nullptr;
+      float* velout = (s == 0 && a.vel) ? a.vel + (size_t)p * prm.field : nullptr;
+      for (int i = tid; i < N; i += NT) {
+        const int r = i / W, c = i % W;
+        const float2 v = z[r * LD + c];
+        float n0, n1;
+        if (s == 0) {
+          n0 = mdt * v.x;
+          n1 = mdt * v.y;
+          if (utraj0) { utraj0[i] = 0.f; utraj0[N + i] = 0.f; }
+          if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
+        } else {
+          const float* u0 = ucur;
+          const float* u1 = ucur + N;
+          const Taps tp = make_taps<BG>((float)r + mdt * v.x, (float)c + mdt * v.y, H, W);
+          n0 = tap_sample<BG>(tp, u0[tp.o00], u0[tp.o10], u0[tp.o01], u0[tp.o11]) + mdt * v.x;
+          n1 = tap_sample<BG>(tp, u1[tp.o00], u1[tp.o10], u1[tp.o01], u1[tp.o11]) + mdt * v.y;
+        }
+        unext[i] = n0;
+        unext[N + i] = n1;
+        if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+      }
+      ucur = unext;
+    }
+    __syncthreads();   // u^S visible to the whole CTA
+
+    // ---- deformed_source = interp(src, u^S)
+    if (a.sdef) {
+      const float* src = a.src + (size_t)(a.src_per_pair ? p : b) * N;
+      float* sd = a.sdef + (size_t)p * N;
+      const float* u0 = ucur;
+      const float* u1 = ucur + N;
+      for (int i = tid; i < N; i += NT) {
+        const int r = i / W, c = i % W;
+        const Taps tp = make_taps<BG>((float)r + u0[i], (float)c + u1[i], H, W);
+        sd[i] = tap_sample<BG>(tp, __ldg(src + tp.o00), __ldg(src + tp.o10), __ldg(src + tp.o01), __ldg(src + tp.o11));
+      }
+    }
+    // ---- strain matrix column t of slice b
+    if (a.S) {
+      for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0.f; cnts_s[i] = 0; }
+      __syncthreads();
+      strain_bin_frame<NT>(ucur, ucur + N, a.tar + (size_t)p * N, reinterpret_cast<const long long*>(a.moments) + 3 * b,
+                           tab_s, n_sectors, H, W, sums_s, cnts_s, tid);
+      strain_store_column<NT>(sums_s, cnts_s, a.S, a.counts, (int)b, t, (int)a.T1, n_sectors, a.n_frames, tid);
+    }
+    __syncthreads();   // z and bins free for the next pair
+  }
+}
+
+template <int H, int W, int NT>
+struct FusedCfg {
+  static int ctas_per_sm() {
+    int per = (int)((224 * 1024) / (ShootSmem<H, W>::bytes + 1024));
+    if (per < 1) per = 1;
+    if (per * NT > 2048) per = 2048 / NT;
+    return per;
+  }
+};
+
+static int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return sms;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+  return sms;
+}
+
+static bool fused_size(int64_t H, int64_t W) { return H == W && (H == 16 || H == 32 || H == 64 || H == 128); }
+
+static int64_t fused_grid(int64_t P, int64_t H) {
+  int per = 1;
+  switch ((int)H) {
+    case 16: per = FusedCfg<16, 16, 128>::ctas_per_sm(); break;
+    case 32: per = FusedCfg<32, 32, 256>::ctas_per_sm(); break;
+    case 64: per = FusedCfg<64, 64, 256>::ctas_per_sm(); break;
+    case 128: per = FusedCfg<128, 128, 512>::ctas_per_sm(); break;
+  }
+  int64_t g = (int64_t)sm_count() * per;
+  return g < P ? g : P;
+}
+
+template <int H, int W, int NT>
+static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
+  const size_t smem = ShootSmem<H, W>::bytes;
+  if (prm.a.background == B2_BG_CLAMP) {
+    B2_CUDA(cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP><<<(unsigned)grid, NT, smem, st>>>(prm);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shoot_fwd_kernel<H, W, NT, B2_BG_ZERO><<<(unsigned)grid, NT, smem, st>>>(prm);
+  }
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------ small elementwise helpers
+__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + b * y[i];
+}
+static int axpby(float* y, const float* x, float a, float b, size_t n, cudaStream_t st) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  axpby_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, x, a, b, n);
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps) {
+  if (B <= 0 || T1 <= 0 || H <= 0 || W <= 0 || num_steps <= 0) return 0;
+  const int64_t P = B * T1, field = 2 * H * W;
+  if (fused_size(H, W)) return (int64_t)align256(sizeof(float) * (size_t)fused_grid(P, H) * 2 * field);
+  // path B: m0 (if not given) + u scratch + m/v buffer + FFT scratch
+  return (int64_t)(3 * align256(sizeof(float) * (size_t)P * field) + align256((size_t)b2_fluid_workspace_bytes(P, H, W)));
+}
+
+extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!args) return B2_E_NULL;
+  const b2_shoot_args& a = *args;
+  if (!a.v0 || !a.u) return B2_E_NULL;
+  if (a.B <= 0 || a.T1 <= 0 || a.H < 2 || a.W < 2) return B2_E_SHAPE;
+  if (a.num_steps < 1 || a.num_steps > 4096 || !(a.gamma > 0.f) || a.alpha < 0.f || a.beta < 0.f || !(a.T > 0.f)) return B2_E_PARAM;
+  if (a.background != B2_BG_CLAMP && a.background != B2_BG_ZERO) return B2_E_PARAM;
+  if (a.sdef && !a.src) return B2_E_NULL;
+  if (a.S && (!a.tar || !a.moments || !a.table)) return B2_E_NULL;
+  if (a.S && (a.n_sectors < 3 || a.n_sectors > kFusedMaxSectors || a.n_frames < 1)) return B2_E_PARAM;
+  const int64_t P = a.B * a.T1, H = a.H, W = a.W, field = 2 * H * W;
+  if (P > ((int64_t)1 << 30)) return B2_E_SHAPE;
+  const int64_t need = b2_shoot_workspace_bytes(a.B, a.T1, H, W, a.num_steps);
+  if (need <= 0) return B2_E_FFTSIZE;
+  if (!workspace || workspace_bytes < need) return B2_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (fused_size(H, W)) {
+    ShootParams prm;
+    prm.a = a;
+    prm.scratch = reinterpret_cast<float*>(workspace);
+    prm.P = P;
+    prm.field = field;
+    const int64_t grid = fused_grid(P, H);
+    switch ((int)H) {
+      case 16: return launch_fused<16, 16, 128>(prm, grid, st);
+      case 32: return launch_fused<32, 32, 256>(prm, grid, st);
+      case 64: return launch_fused<64, 64, 256>(prm, grid, st);
+      case 128: return launch_fused<128, 128, 512>(prm, grid, st);
+    }
+    return B2_E_FFTSIZE;
+  }
+
+  // ---- path B: op-level sequence
+  if (b2_fluid_workspace_bytes(P, H, W) <= 0) return B2_E_FFTSIZE;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  const size_t fbytes = align256(sizeof(float) * (size_t)P * field);
+  const float* m0 = a.v0;
+  if (!a.v0_is_momentum) {
+    float* m0w = a.m0 ? a.m0 : reinterpret_cast<float*>(ws);
+    if (int e = fluid_apply_impl(a.v0, m0w, P, H, W, a.alpha, a.beta, a.gamma, 0, ws + 3 * fbytes,
+                                 b2_fluid_workspace_bytes(P, H, W), st))
+      return e;
+    m0 = m0w;
+  }
+  float* uscr = reinterpret_cast<float*>(ws + fbytes);
+  float* mv = reinterpret_cast<float*>(ws + 2 * fbytes);
+  void* fws = ws + 3 * fbytes;
+  const int64_t fws_bytes = b2_fluid_workspace_bytes(P, H, W);
+  const int S = a.num_steps;
+  const float dt = a.T / (float)S;
+  const size_t n = (size_t)P * field;
+  const float* ucur = nullptr;
+  for (int s = 0; s < S; ++s) {
+    float* vbuf = a.traj ? a.traj + (size_t)(s * 2 + 1) * n : mv;
+    if (s == 0) {
+      if (int e = fluid_apply_impl(m0, vbuf, P, H, W, a.alpha, a.beta, a.gamma, 1, fws, fws_bytes, st)) return e;
+      if (a.vel) B2_CUDA(cudaMemcpyAsync(a.vel, vbuf, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+      if (a.traj) B2_CUDA(cudaMemsetAsync(a.traj, 0, sizeof(float) * n, st));
+    } else {
+      if (int e = b2_adstar_fwd(ucur, m0, vbuf, P, H, W, a.background, stream)) return e;
+      if (int e = fluid_apply_impl(vbuf, vbuf, P, H, W, a.alpha, a.beta, a.gamma, 1, fws, fws_bytes, st)) return e;
+    }
+    float* unext;
+    if (a.traj) unext = (s + 1 < S) ? a.traj + (size_t)((s + 1) * 2) * n : a.u;
+    else unext = (((S - (s + 1)) & 1) == 0) ? a.u : uscr;
+    if (s == 0) {
+      if (int e = axpby(unext, vbuf, -dt, 0.f, n, st)) return e;
+    } else {
+      if (int e = b2_compose_fwd(ucur, vbuf, unext, P, H, W, -dt, a.background, stream)) return e;
+    }
+    ucur = unext;
+  }
+  if (a.sdef) {
+    if (a.src_per_pair) {
+      if (int e = b2_interp_fwd(a.src, a.u, a.sdef, P, P, P, 1, H, W, 1.f, a.background, stream)) return e;
+    } else {
+      for (int64_t b = 0; b < a.B; ++b) {   // src broadcast over the T1 pairs of a slice
+        if (int e = b2_interp_fwd(a.src + (size_t)b * H * W, a.u + (size_t)b * a.T1 * field,
+                                  a.sdef + (size_t)b * a.T1 * H * W, a.T1, 1, a.T1, 1, H, W, 1.f, a.background, stream))
+          return e;
+      }
+    }
+  }
+  if (a.S) {
+    if (int e = b2_strain_sector_fwd(a.u, a.tar, a.moments, a.table, a.S, a.counts, a.B, a.T1, H, W, a.n_sectors,
+                                     a.n_frames, stream))
+      return e;
+  }
+  return B2_OK;
+}
+
+extern "C" int64_t b2_shoot_bwd_workspace_bytes(int64_t P, int64_t H, int64_t W) {
+  if (P <= 0 || H <= 0 || W <= 0) return 0;
+  const int64_t fw = b2_fluid_workspace_bytes(P, H, W);
+  return (int64_t)(5 * align256(sizeof(float) * (size_t)P * 2 * H * W) + align256((size_t)fw));
+}
+
+extern "C" int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0, const float* m0, const float* traj,
+                            float* gv0, int64_t P, int64_t H, int64_t W, int num_steps, float alpha, float beta,
+                            float gamma, float T, int background, int v0_is_momentum, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  if (!m0 || !traj || !gv0) return B2_E_NULL;
+  if (P <= 0 || H < 2 || W < 2 || P > ((int64_t)1 << 30)) return B2_E_SHAPE;
+  if (num_steps < 1 || !(gamma > 0.f) || !(T > 0.f)) return B2_E_PARAM;
+  if (!workspace || workspace_bytes < b2_shoot_bwd_workspace_bytes(P, H, W)) return B2_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)P * 2 * H * W, fbytes = align256(sizeof(float) * n);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  float* g_u = reinterpret_cast<float*>(ws);                  // dL/du_{s+1}
+  float* g_uc = reinterpret_cast<float*>(ws + fbytes);        // compose part of dL/du_s
+  float* g_v = reinterpret_cast<float*>(ws + 2 * fbytes);     // dL/dv_s, then dL/dm_s
+  float* g_m0 = reinterpret_cast<float*>(ws + 3 * fbytes);    // accumulated dL/dm0
+  float* wbuf = reinterpret_cast<float*>(ws + 4 * fbytes);    // adstar workspace: m0 o (id + u_s)
+  void* fws = ws + 5 * fbytes;
+  const int64_t fws_bytes = b2_fluid_workspace_bytes(P, H, W);
+  const float dt = T / (float)num_steps;
+
+  if (gu) B2_CUDA(cudaMemcpyAsync(g_u, gu, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  else B2_CUDA(cudaMemsetAsync(g_u, 0, sizeof(float) * n, st));
+  if (gm0) B2_CUDA(cudaMemcpyAsync(g_m0, gm0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  else B2_CUDA(cudaMemsetAsync(g_m0, 0, sizeof(float) * n, st));
+
+  for (int s = num_steps - 1; s >= 0; --s) {
+    const float* u_s = traj + (size_t)(s * 2) * n;
+    const float* v_s = traj + (size_t)(s * 2 + 1) * n;
+    // u_{s+1} = interp(u_s, v_s, -dt) - dt v_s
+    if (int e = b2_compose_bwd(g_u, u_s, v_s, s > 0 ? g_uc : nullptr, g_v, P, H, W, -dt, background, stream)) return e;
+    if (s == 0 && gvel) {
+      if (int e = axpby(g_v, gvel, 1.f, 1.f, n, st)) return e;
+    }
+    // v_s = sharp(m_s), self-adjoint
+    if (int e = fluid_apply_impl(g_v, g_v, P, H, W, alpha, beta, gamma, 1, fws, fws_bytes, st)) return e;
+    if (s == 0) {
+      // m_0 = Ad*_0 m0 = m0 exactly (u_0 = 0)
+      if (int e = axpby(g_m0, g_v, 1.f, 1.f, n, st)) return e;
+    } else {
+      // m_s = Ad*_{u_s} m0: du -> g_u (dead after compose_bwd), dm0 accumulated into g_m0
+      if (int e = adstar_bwd_impl(g_v, u_s, m0, g_u, g_m0, wbuf, P, H, W, background, /*zero_dm0=*/false, st)) return e;
+      if (int e = axpby(g_u, g_uc, 1.f, 1.f, n, st)) return e;
+    }
+  }
+  if (v0_is_momentum) {   // the input was m0 itself: return dL/dm0
+    B2_CUDA(cudaMemcpyAsync(gv0, g_m0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    return B2_OK;
+  }
+  // dL/dv0 = flat(dL/dm0)
+  return fluid_apply_impl(g_m0, gv0, P, H, W, alpha, beta, gamma, 0, fws, fws_bytes, st);
+}
+
+extern "C" int b2_device_sm_count(int device) {
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  return sms;
+}
+
+extern "C" int b2_version(void) { return 100; }
+
+extern "C" const char* b2_error_string(int code) {
+  switch (code) {
+    case B2_OK: return "ok";
+    case B2_E_NULL: return "required pointer is NULL";
+    case B2_E_SHAPE: return "non-positive or unsupported dimension";
+    case B2_E_BCAST: return "batch sizes do not broadcast";
+    case B2_E_FFTSIZE: return "H/W not a supported FFT size (square 16..128, 256x256, 64x128, 128x64, 128x256, 256x128)";
+    case B2_E_PARAM: return "bad scalar parameter";
+    case B2_E_WORKSPACE: return "workspace missing or too small";
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown b2lddmm error";
+}

@@ -1,0 +1,232 @@
+// Mask moments, integer-exact sector map, strain-matrix reduction and its adjoint.
+// [SPEC] SURVEY.md 8a rows 17-18; sector count / order pinned by
+// /root/reference/modules/data/utils/DENSE_utils.py:177-295 and augmentation/affine.py:52-87.
+#include <math.h>
+
+#include "strain.cuh"
+
+namespace b2 {
+
+constexpr int kNTS = 256;
+
+__global__ void __launch_bounds__(kNTS)
+mask_moments_kernel(const float* __restrict__ mask0, unsigned long long* __restrict__ mom, int H, int W) {
+  const int b = blockIdx.y, N = H * W;
+  const float* m = mask0 + (size_t)b * N;
+  unsigned long long cnt = 0, sx = 0, sy = 0;
+  for (int x = blockIdx.x * kNTS + threadIdx.x; x < N; x += gridDim.x * kNTS) {
+    if (m[x] > 0.5f) {
+      const int r = x / W;
+      cnt += 1; sx += (unsigned)r; sy += (unsigned)(x - r * W);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    sx += __shfl_down_sync(0xffffffffu, sx, o);
+    sy += __shfl_down_sync(0xffffffffu, sy, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    atomicAdd(mom + 3 * b + 0, cnt);
+    atomicAdd(mom + 3 * b + 1, sx);
+    atomicAdd(mom + 3 * b + 2, sy);
+  }
+}
+
+__global__ void __launch_bounds__(kNTS)
+sector_map_kernel(const long long* __restrict__ mom, const int32_t* __restrict__ table, int32_t* __restrict__ sector,
+                  int H, int W, int n_sectors) {
+  extern __shared__ int32_t tab_s[];
+  for (int i = threadIdx.x; i < 2 * n_sectors; i += kNTS) tab_s[i] = table[i];
+  __syncthreads();
+  const int b = blockIdx.y, N = H * W;
+  const long long cnt = mom[3 * b], sx = mom[3 * b + 1], sy = mom[3 * b + 2];
+  for (int x = blockIdx.x * kNTS + threadIdx.x; x < N; x += gridDim.x * kNTS) {
+    const int r = x / W, c = x - r * W;
+    sector[(size_t)b * N + x] = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors);
+  }
+}
+
+// one CTA per (slice b, frame t)
+__global__ void __launch_bounds__(kNTS)
+strain_sector_fwd_kernel(const float* __restrict__ u, const float* __restrict__ tar, const long long* __restrict__ mom,
+                         const int32_t* __restrict__ table, float* __restrict__ S, int32_t* __restrict__ counts,
+                         int B, int T1, int H, int W, int n_sectors, int n_frames) {
+  extern __shared__ int32_t smem_i[];
+  int32_t* tab_s = smem_i;
+  float* sums_s = reinterpret_cast<float*>(smem_i + 2 * n_sectors);
+  int* cnts_s = smem_i + 3 * n_sectors;
+  const int tid = threadIdx.x;
+  const int N = H * W;
+  for (int i = tid; i < 2 * n_sectors; i += kNTS) tab_s[i] = table[i];
+  for (long long pt = blockIdx.x; pt < (long long)B * T1; pt += gridDim.x) {
+    const int b = (int)(pt / T1), t = (int)(pt % T1);
+    __syncthreads();
+    for (int i = tid; i < n_sectors; i += kNTS) { sums_s[i] = 0.f; cnts_s[i] = 0; }
+    __syncthreads();
+    const float* u0 = u + (size_t)pt * 2 * N;
+    strain_bin_frame<kNTS>(u0, u0 + N, tar + (size_t)pt * N, mom + 3 * b, tab_s, n_sectors, H, W, sums_s, cnts_s, tid);
+    strain_store_column<kNTS>(sums_s, cnts_s, S, counts, b, t, T1, n_sectors, n_frames, tid);
+  }
+}
+
+// Adjoint: du accumulated with atomics (du zero-filled by the caller).
+__global__ void __launch_bounds__(kNTS)
+strain_sector_bwd_kernel(const float* __restrict__ gS, const float* __restrict__ u, const float* __restrict__ tar,
+                         const long long* __restrict__ mom, const int32_t* __restrict__ table,
+                         const int32_t* __restrict__ counts, float* __restrict__ du,
+                         int B, int T1, int H, int W, int n_sectors, int n_frames) {
+  extern __shared__ int32_t smem_i[];
+  int32_t* tab_s = smem_i;
+  float* gk_s = reinterpret_cast<float*>(smem_i + 2 * n_sectors);   // dL/dEcc per member pixel of sector k
+  const int tid = threadIdx.x;
+  const int N = H * W;
+  for (int i = tid; i < 2 * n_sectors; i += kNTS) tab_s[i] = table[i];
+  for (long long pt = blockIdx.x; pt < (long long)B * T1; pt += gridDim.x) {
+    const int b = (int)(pt / T1), t = (int)(pt % T1);
+    __syncthreads();
+    for (int k = tid; k < n_sectors; k += kNTS) {
+      const float* row = gS + ((size_t)b * n_sectors + k) * n_frames;
+      float g = (t < n_frames) ? row[t] : 0.f;
+      if (t == T1 - 1)
+        for (int tt = T1; tt < n_frames; ++tt) g += row[tt];
+      const int cn = counts[((size_t)b * n_sectors + k) * T1 + t];
+      gk_s[k] = g / (float)max(cn, 1);
+    }
+    __syncthreads();
+    const long long* mo = mom + 3 * b;
+    const long long cnt = mo[0], sx = mo[1], sy = mo[2];
+    float c0, c1;
+    centroid_from_moments(mo, H, W, c0, c1);
+    const float* u0 = u + (size_t)pt * 2 * N;
+    const float* u1 = u0 + N;
+    const float* mask = tar + (size_t)pt * N;
+    float* d0 = du + (size_t)pt * 2 * N;
+    float* d1 = d0 + N;
+    for (int x = tid; x < N; x += kNTS) {
+      if (!(mask[x] > 0.5f)) continue;
+      const int r = x / W, c = x - r * W;
+      const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors);
+      if (k < 0) continue;
+      int rlo, rhi, clo, chi; float sr, sc;
+      diff_idx(r, H, rlo, rhi, sr);
+      diff_idx(c, W, clo, chi, sc);
+      const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
+      const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+      const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
+      const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+      EccTerms e; float ecc;
+      if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[x], (float)c + u1[x], c0, c1, e, ecc)) continue;
+      const float gq = 0.5f * gk_s[k];
+      if (gq == 0.f) continue;
+      const float e0 = -e.n1, e1 = e.n0;
+      const float g_t0 = gq * 2.f * e.t0 / e.den, g_t1 = gq * 2.f * e.t1 / e.den;
+      const float g_den = -gq * e.q / e.den;
+      const float g_rad2 = g_den * e.det * e.det;
+      const float g_det = g_den * e.rad2 * 2.f * e.det;
+      float g_G11 = g_t0 * e0 + g_det * e.G00;
+      float g_G01 = -g_t0 * e1 - g_det * e.G10;
+      float g_G00 = g_t1 * e1 + g_det * e.G11;
+      float g_G10 = -g_t1 * e0 - g_det * e.G01;
+      const float g_e0 = g_t0 * e.G11 - g_t1 * e.G10;
+      const float g_e1 = -g_t0 * e.G01 + g_t1 * e.G00;
+      const float g_n0 = 2.f * e.n0 * g_rad2 + g_e1;
+      const float g_n1 = 2.f * e.n1 * g_rad2 - g_e0;
+      atomicAdd(d0 + x, g_n0);
+      atomicAdd(d1 + x, g_n1);
+      // G00 = 1 + d0 u0, G10 = d0 u1 (row differences); G01 = d1 u0, G11 = 1 + d1 u1 (col differences)
+      atomicAdd(d0 + rhi * W + c, sr * g_G00); atomicAdd(d0 + rlo * W + c, -sr * g_G00);
+      atomicAdd(d1 + rhi * W + c, sr * g_G10); atomicAdd(d1 + rlo * W + c, -sr * g_G10);
+      atomicAdd(d0 + r * W + chi, sc * g_G01); atomicAdd(d0 + r * W + clo, -sc * g_G01);
+      atomicAdd(d1 + r * W + chi, sc * g_G11); atomicAdd(d1 + r * W + clo, -sc * g_G11);
+    }
+  }
+}
+
+static int check_strain(int64_t B, int64_t T1, int64_t H, int64_t W, int n_sectors, int n_frames) {
+  if (B <= 0 || T1 <= 0 || H < 2 || W < 2 || H * W > ((int64_t)1 << 30) || B * T1 > ((int64_t)1 << 40)) return B2_E_SHAPE;
+  if (n_sectors < 3 || n_sectors > kMaxSectors || n_frames < 1) return B2_E_PARAM;
+  return B2_OK;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_sector_table_host(int n_sectors, int32_t* table_host) {
+  if (!table_host) return B2_E_NULL;
+  if (n_sectors < 3 || n_sectors > kMaxSectors) return B2_E_PARAM;
+  const double q = 1048576.0, two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < n_sectors; ++k) {
+    const double ang = two_pi * (double)k / (double)n_sectors;
+    table_host[2 * k] = (int32_t)llrint(q * sin(ang));
+    table_host[2 * k + 1] = (int32_t)llrint(q * cos(ang));
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_mask_moments(const float* mask0, int64_t* moments, int64_t B, int64_t H, int64_t W, void* stream) {
+  if (!mask0 || !moments) return B2_E_NULL;
+  if (B <= 0 || H < 1 || W < 1 || H * W > ((int64_t)1 << 30)) return B2_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  B2_CUDA(cudaMemsetAsync(moments, 0, sizeof(int64_t) * 3 * (size_t)B, st));
+  const int64_t N = H * W;
+  int gx = (int)((N + kNTS * 8 - 1) / (kNTS * 8));
+  if (gx < 1) gx = 1;
+  for (int64_t b0 = 0; b0 < B; b0 += kMaxGridY) {
+    const int64_t bn = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+    mask_moments_kernel<<<dim3(gx, (unsigned)bn), kNTS, 0, st>>>(mask0 + (size_t)b0 * N,
+                                                                reinterpret_cast<unsigned long long*>(moments) + 3 * b0,
+                                                                (int)H, (int)W);
+    B2_CHECK_LAUNCH();
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_sector_map_i32(const int64_t* moments, const int32_t* table, int32_t* sector, int64_t B, int64_t H,
+                                 int64_t W, int n_sectors, void* stream) {
+  if (!moments || !table || !sector) return B2_E_NULL;
+  if (B <= 0 || H < 1 || W < 1 || H * W > ((int64_t)1 << 30)) return B2_E_SHAPE;
+  if (n_sectors < 3 || n_sectors > kMaxSectors) return B2_E_PARAM;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = H * W;
+  int gx = (int)((N + kNTS * 4 - 1) / (kNTS * 4));
+  if (gx < 1) gx = 1;
+  for (int64_t b0 = 0; b0 < B; b0 += kMaxGridY) {
+    const int64_t bn = (B - b0 < kMaxGridY) ? B - b0 : kMaxGridY;
+    sector_map_kernel<<<dim3(gx, (unsigned)bn), kNTS, sizeof(int32_t) * 2 * n_sectors, st>>>(
+        reinterpret_cast<const long long*>(moments) + 3 * b0, table, sector + (size_t)b0 * N, (int)H, (int)W, n_sectors);
+    B2_CHECK_LAUNCH();
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_strain_sector_fwd(const float* u, const float* tar, const int64_t* moments, const int32_t* table,
+                                    float* S, int32_t* counts, int64_t B, int64_t T1, int64_t H, int64_t W,
+                                    int n_sectors, int n_frames, void* stream) {
+  if (!u || !tar || !moments || !table || !S) return B2_E_NULL;
+  if (int e = check_strain(B, T1, H, W, n_sectors, n_frames)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t grid = B * T1;
+  if (grid > (1 << 20)) grid = 1 << 20;
+  strain_sector_fwd_kernel<<<(unsigned)grid, kNTS, sizeof(int32_t) * 4 * n_sectors, st>>>(
+      u, tar, reinterpret_cast<const long long*>(moments), table, S, counts, (int)B, (int)T1, (int)H, (int)W,
+      n_sectors, n_frames);
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+extern "C" int b2_strain_sector_bwd(const float* gS, const float* u, const float* tar, const int64_t* moments,
+                                    const int32_t* table, const int32_t* counts, float* du, int64_t B, int64_t T1,
+                                    int64_t H, int64_t W, int n_sectors, int n_frames, void* stream) {
+  if (!gS || !u || !tar || !moments || !table || !counts || !du) return B2_E_NULL;
+  if (int e = check_strain(B, T1, H, W, n_sectors, n_frames)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  B2_CUDA(cudaMemsetAsync(du, 0, sizeof(float) * 2 * (size_t)B * T1 * H * W, st));
+  int64_t grid = B * T1;
+  if (grid > (1 << 20)) grid = 1 << 20;
+  strain_sector_bwd_kernel<<<(unsigned)grid, kNTS, sizeof(int32_t) * 3 * n_sectors, st>>>(
+      gS, u, tar, reinterpret_cast<const long long*>(moments), table, counts, du, (int)B, (int)T1, (int)H, (int)W,
+      n_sectors, n_frames);
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}

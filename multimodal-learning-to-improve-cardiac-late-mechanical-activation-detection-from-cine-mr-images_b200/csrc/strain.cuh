@@ -1,0 +1,58 @@
+// Fused Jacobian-stencil strain + sector-binning device code ([SPEC] SURVEY.md A.7/A.8).
+// Shared by strain.cu (op level) and shoot.cu (fused epilogue).
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kMaxSectors = 1024;
+
+// Accumulate one (slice, frame) into shared-memory bins.  `u0/u1` point at the
+// displacement of this pair, `mask` at its target-frame mask; all threads of the
+// CTA call this; bins must be zeroed + synced before and are synced after.
+template <int NT>
+__device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u1, const float* __restrict__ mask,
+                                                 const long long* mom, const int32_t* tab_s, int n_sectors,
+                                                 int H, int W, float* sums_s, int* cnts_s, int tid) {
+  const long long cnt = mom[0], sx = mom[1], sy = mom[2];
+  float c0, c1;
+  centroid_from_moments(mom, H, W, c0, c1);
+  const int N = H * W;
+  for (int x = tid; x < N; x += NT) {
+    if (!(mask[x] > 0.5f)) continue;
+    const int r = x / W, c = x - r * W;
+    const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors);
+    if (k < 0) continue;
+    int rlo, rhi, clo, chi; float sr, sc;
+    diff_idx(r, H, rlo, rhi, sr);
+    diff_idx(c, W, clo, chi, sc);
+    const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
+    const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+    const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
+    const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+    EccTerms e; float ecc;
+    if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[x], (float)c + u1[x], c0, c1, e, ecc)) continue;
+    atomicAdd(&sums_s[k], ecc);
+    atomicAdd(&cnts_s[k], 1);
+  }
+  __syncthreads();
+}
+
+// Write column t of S (B,1,K,n_frames) from the bins, with edge-padding of the
+// last frame and cropping beyond n_frames (align_n_frames_to semantics).
+template <int NT>
+__device__ __forceinline__ void strain_store_column(const float* sums_s, const int* cnts_s, float* __restrict__ S,
+                                                    int32_t* __restrict__ counts, int b, int t, int T1,
+                                                    int n_sectors, int n_frames, int tid) {
+  for (int k = tid; k < n_sectors; k += NT) {
+    const int cn = cnts_s[k];
+    const float v = sums_s[k] / (float)max(cn, 1);
+    float* row = S + ((size_t)b * n_sectors + k) * n_frames;
+    if (t < n_frames) row[t] = v;
+    if (t == T1 - 1)
+      for (int tt = T1; tt < n_frames; ++tt) row[tt] = v;
+    if (counts) counts[((size_t)b * n_sectors + k) * T1 + t] = cn;
+  }
+}
+
+}  // namespace b2

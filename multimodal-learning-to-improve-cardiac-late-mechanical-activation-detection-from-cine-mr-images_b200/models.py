@@ -1,0 +1,131 @@
+"""``models``-compatible shim: the modules the reference's trainers instantiate.
+
+The reference does ``from models import build_model`` (/root/reference/main.py:42-46)
+but ships no ``models`` package, so the networks that
+*produce* the initial velocity are stand-ins (plain torch/cuDNN - library code,
+outside the measured hot path).  What is pinned by the reference and kept
+exactly is the interface: ``build_model(model_config)`` dispatching on
+``model_config['type']`` (/root/reference/configs/config.json:110,117),
+``forward_volume(src_vol, tar_vol)`` and its dict keys
+(joint_registration_strainmat_LMA.py:307,314-318), the pairwise
+``model(src, tar)`` dict and ``.sigma`` (reg_trainer.py:45,222-225,230) and
+``LMA_model(strain_matrix) -> {'TOS': (B,126)}`` (joint_registration_strainmat_LMA.py:308).
+Everything between ``v0`` and the returned dict is the B200-native hot path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .ops import FluidMetric
+from .shooting import shoot_warp_pairs, shoot_warp_strain
+
+
+class VelocityNet(nn.Module):
+    """Small encoder-decoder mapping a (src, tar) pair to an initial velocity v0 (P,2,H,W)."""
+
+    def __init__(self, width: int = 16, max_velocity: float = 3.0):
+        super().__init__()
+        self.enc1 = nn.Conv2d(2, width, 3, padding=1)
+        self.enc2 = nn.Conv2d(width, 2 * width, 3, stride=2, padding=1)
+        self.mid = nn.Conv2d(2 * width, 2 * width, 3, padding=1)
+        self.dec1 = nn.Conv2d(3 * width, width, 3, padding=1)
+        self.out = nn.Conv2d(width, 2, 3, padding=1)
+        self.max_velocity = max_velocity
+        nn.init.normal_(self.out.weight, std=1e-3)
+        nn.init.zeros_(self.out.bias)
+
+    def forward(self, src, tar):
+        x = torch.cat([src, tar], dim=1)
+        e1 = F.relu(self.enc1(x))
+        e2 = F.relu(self.enc2(e1))
+        m = F.relu(self.mid(e2))
+        up = F.interpolate(m, size=e1.shape[-2:], mode="bilinear", align_corners=False)
+        d1 = F.relu(self.dec1(torch.cat([up, e1], dim=1)))
+        return self.max_velocity * torch.tanh(self.out(d1))
+
+
+def svd_smooth(S: torch.Tensor, rank: int) -> torch.Tensor:
+    """Rank truncation of each (sectors x frames) strain matrix.
+
+    Same operation as ``SVDDenoise`` (/root/reference/modules/data/utils/DENSE_utils.py:11-14),
+    selected by ``strainmat_smoothing_method: "SVD"`` (configs/config.json:113-114).
+    """
+    U, s, Vh = torch.linalg.svd(S, full_matrices=False)
+    s = torch.cat([s[..., :rank], torch.zeros_like(s[..., rank:])], dim=-1)
+    return (U * s.unsqueeze(-2)) @ Vh
+
+
+class JointRegisterStrainMatNet(nn.Module):
+    """Registration network + geodesic shooting + strain matrix (``forward_volume``)."""
+
+    def __init__(self, config: dict | None = None):
+        super().__init__()
+        config = dict(config or {})
+        self.n_strain_matrix_frames = int(config.get("n_strain_matrix_frames", 40))
+        self.n_sectors = int(config.get("n_sectors", 126))
+        self.num_steps = int(config.get("num_steps", 10))
+        self.sigma = float(config.get("sigma", 0.03))
+        self.smoothing = config.get("strainmat_smoothing_method", None)
+        self.smoothing_rank = int(config.get("strainmat_smoothing_SVD_rank", 5))
+        self.metric = FluidMetric(config.get("fluid_params", (1.0, 0.1, 0.05)))
+        self.velocity_net = VelocityNet(int(config.get("velocity_net_width", 16)),
+                                        float(config.get("max_velocity", 3.0)))
+
+    def forward(self, src, tar):
+        """Pairwise contract: src, tar (P,1,H,W) -> displacement / velocity / momentum / deformed_source."""
+        v0 = self.velocity_net(src, tar)
+        return shoot_warp_pairs(v0, src, tar, self.metric, self.num_steps)
+
+    def forward_volume(self, src_vol, tar_vol):
+        """src_vol, tar_vol (B,1,T-1,H,W) -> {'strain_matrix','deformed_source','velocity','momentum',...}."""
+        B, C, T1, H, W = tar_vol.shape
+        src0 = src_vol[:, :, :1].expand(B, C, T1, H, W)
+        v0 = self.velocity_net(src0.reshape(B * T1, C, H, W), tar_vol.reshape(B * T1, C, H, W))
+        out = shoot_warp_strain(v0, src_vol, tar_vol, self.metric, self.num_steps,
+                                n_sectors=self.n_sectors, n_frames=self.n_strain_matrix_frames)
+        if self.smoothing == "SVD":
+            out["strain_matrix"] = svd_smooth(out["strain_matrix"], self.smoothing_rank)
+        return out
+
+
+class NetStrainMat2LMA(nn.Module):
+    """Strain matrix (B,1,126,40) -> {'TOS': (B,126)}  (configs/config.json:116-125)."""
+
+    def __init__(self, config: dict | None = None):
+        super().__init__()
+        config = dict(config or {})
+        n_layers = int(config.get("num_conv_layers", 3))
+        ch = int(config.get("inner_conv_channel_num", 16))
+        cin = int(config.get("input_channel_num", 1))
+        self.n_frames = int(config.get("n_frames", 40))
+        self.n_sectors = int(config.get("n_sectors", 126))
+        self.n_classes = int(config.get("n_classes", 1))
+        layers = []
+        for i in range(n_layers):
+            layers += [nn.Conv2d(cin if i == 0 else ch, ch, 3, padding=1), nn.ReLU(inplace=True)]
+        self.features = nn.Sequential(*layers)
+        self.head = nn.Conv2d(ch, self.n_classes, (1, self.n_frames))
+
+    def forward(self, strain_matrix):
+        x = self.features(strain_matrix)
+        y = self.head(x)                        # (B, n_classes, n_sectors, 1)
+        tos = y.squeeze(-1)
+        if self.n_classes == 1:
+            tos = tos.squeeze(1)                # (B, n_sectors)
+        return {"TOS": tos}
+
+
+_REGISTRY = {
+    "JointRegisterStrainMatNet": JointRegisterStrainMatNet,
+    "NetStrainMat2LMA": NetStrainMat2LMA,
+}
+
+
+def build_model(model_config: dict) -> nn.Module:
+    """``models.build_model`` (/root/reference/main.py:42-46): dispatch on ``model_config['type']``."""
+    mtype = model_config["type"]
+    if mtype not in _REGISTRY:
+        raise NotImplementedError(f"model type {mtype!r} not implemented")
+    return _REGISTRY[mtype](model_config)

@@ -1,0 +1,93 @@
+"""Oracle for the callers either side of the hot path (TEST INFRASTRUCTURE).
+
+Restates the in-tree [REF] pieces (pair split, frame alignment, the registration
+loss) and wires the operator oracle into the ``forward_volume`` / pairwise
+contracts the trainers consume.  ``tests/golden/make_golden.py`` checks the
+[REF] restatements against the reference's own code imported from
+/root/reference and commits the resulting vectors.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .lddmm import Conventions, DEFAULT, FluidMetric, interp, shoot
+from .strain import N_SECTORS, strain_matrix
+
+
+def split_vol_to_registration_pairs(vol, split_method: str = "Lagrangian", output_dim: int = 3):
+    """/root/reference/modules/data/__init__.py:93-121."""
+    B, C, T, H, W = vol.shape
+    assert T > 1, f"n_frames should be larger than 1, but got {T}"
+    if split_method == "Lagrangian":
+        src = vol[:, :, :1].repeat(1, 1, T - 1, 1, 1)
+        tar = vol[:, :, 1:]
+    elif split_method == "Eulerian":
+        src = vol[:, :, :-1]
+        tar = vol[:, :, 1:]
+    else:
+        raise ValueError(f"Unrecognized split_method: {split_method}")
+    if output_dim == 2:
+        src = src.reshape(B * (T - 1), C, H, W)
+        tar = tar.reshape(B * (T - 1), C, H, W)
+    return src, tar
+
+
+def align_n_frames_to(volume: np.ndarray, n_target_frames: int, frame_idx: int = -1,
+                      padding_method: str = "edge"):
+    """/root/reference/modules/data/datareader/DENSE_IO_utils.py:2-46."""
+    n = volume.shape[frame_idx]
+    if n >= n_target_frames:
+        sl = [slice(None)] * volume.ndim
+        sl[frame_idx] = slice(0, n_target_frames)
+        return volume[tuple(sl)]
+    pads = [(0, 0)] * volume.ndim
+    pads[frame_idx] = (0, n_target_frames - n)
+    return np.pad(volume, pads, mode=padding_method)
+
+
+def forward_pairs(v0, src, tar, metric: FluidMetric, num_steps: int = 10,
+                  conv: Conventions = DEFAULT):
+    """Pairwise contract of /root/reference/modules/trainer/reg_trainer.py:45,222-225.
+
+    v0: (P,2,H,W) initial velocity (stands in for the missing network), src/tar (P,1,H,W).
+    """
+    m0, vel, u = shoot(metric, v0, num_steps, conv=conv)
+    return {
+        "displacement": u,
+        "velocity": vel,
+        "momentum": m0,
+        "deformed_source": interp(src, u, 1.0, conv),
+    }
+
+
+def forward_volume(v0, src_vol, tar_vol, metric: FluidMetric, num_steps: int = 10,
+                   n_sectors: int = N_SECTORS, n_frames: int | None = 40,
+                   conv: Conventions = DEFAULT):
+    """``forward_volume`` contract of joint_registration_strainmat_LMA.py:307,314-318.
+
+    v0: (B*(T-1), 2, H, W) ordered slice-major; src_vol, tar_vol: (B,1,T-1,H,W).
+    """
+    B, C, T1, H, W = tar_vol.shape
+    assert C == 1
+    src = src_vol.reshape(B * T1, 1, H, W)
+    out = forward_pairs(v0, src, tar_vol.reshape(B * T1, 1, H, W), metric, num_steps, conv)
+    u = out["displacement"]
+    S = strain_matrix(u.reshape(B, T1, 2, H, W), tar_vol[:, 0], src_vol[:, 0, 0],
+                      n_sectors, n_frames, conv)
+    return {
+        "strain_matrix": S,
+        "deformed_source": out["deformed_source"].reshape(B, 1, T1, H, W),
+        "velocity": out["velocity"],
+        "momentum": out["momentum"],
+        "displacement": u,
+    }
+
+
+def registration_reconstruction_loss(pred, target, sigma=0.03, regularization_weight=0.1):
+    """/root/reference/modules/loss/registration_losses.py:22-28."""
+    Sdef = pred["deformed_source"]
+    tar = target["registration_target"]
+    recon = torch.mean((tar - Sdef) ** 2)
+    reg = (pred["velocity"] * pred["momentum"]).sum() / tar.numel()
+    return 0.5 * recon / (sigma * sigma) + reg * regularization_weight
