@@ -1,0 +1,46 @@
+import pathlib
+import sys
+
+import pytest
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package (hyphenated directory name -> importlib)."""
+    import __graft_entry__ as g
+    return g.load_package()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle as o
+    return o
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return np.load(ROOT / "tests" / "golden" / "ref_boundary.npz")
+
+
+@pytest.fixture(scope="session")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    """max |a-b| relative to the scale of the reference field b."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)

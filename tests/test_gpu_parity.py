@@ -1,0 +1,291 @@
+"""GPU parity tests: every CUDA op, called through the lagomorph-compatible Python surface
+(ctypes -> C ABI of include/b2lddmm.h), against the torch-CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): 1e-5 relative for fp32 fields, measured as
+max|a-b| / max|b| (error relative to the field's scale); bit-exact for integer work
+(sector ids, mask moments, member counts).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GTOL = 2e-5      # gradients accumulated with float atomics (order non-deterministic)
+PARAMS = (1.0, 0.1, 0.05)
+
+
+def _rand(*s, seed=0):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
+
+
+def _grads(fn, inputs, gout):
+    ins = [x.detach().clone().requires_grad_(True) for x in inputs]
+    out = fn(*ins)
+    out.backward(gout.to(out.device))
+    return out.detach(), [x.grad for x in ins]
+
+
+def _check_op(dev, f_gpu, f_cpu, inputs, seed=100, tol=TOL, gtol=GTOL):
+    out_c, g_c = _grads(f_cpu, inputs, gout := _rand(*f_cpu(*inputs).shape, seed=seed))
+    out_g, g_g = _grads(f_gpu, [x.to(dev) for x in inputs], gout)
+    assert relerr(out_g, out_c) < tol, f"forward {relerr(out_g, out_c):.2e}"
+    for i, (a, b) in enumerate(zip(g_g, g_c)):
+        assert a is not None and relerr(a, b) < gtol, f"grad[{i}] {relerr(a, b):.2e}"
+
+
+@pytest.mark.parametrize("bg", ["clamp", "zero"])
+@pytest.mark.parametrize("shape", [(3, 2, 16, 16), (2, 1, 33, 47), (2, 3, 128, 128)])
+def test_interp(pkg, oracle, dev, bg, shape):
+    P, C, H, W = shape
+    I, u = _rand(P, C, H, W, seed=1), 3.0 * _rand(P, 2, H, W, seed=2)
+    u[0, :, 0, 0] = 500.0          # far out of bounds
+    u[0, :, 1, 1] = -500.0
+    conv = oracle.Conventions(background=bg)
+    _check_op(dev, lambda a, b: pkg.interp(a, b, 0.8, bg), lambda a, b: oracle.interp(a, b, 0.8, conv), [I, u])
+
+
+def test_interp_exact_cases(pkg, dev):
+    I = _rand(2, 2, 20, 24, seed=3).to(dev)
+    z = torch.zeros(2, 2, 20, 24, device=dev)
+    assert torch.equal(pkg.interp(I, z), I)                       # interp(I, 0) == I exactly
+    u = torch.zeros(2, 2, 20, 24, device=dev)
+    u[:, 0], u[:, 1] = 2.0, -3.0
+    rr = (torch.arange(20, device=dev).view(20, 1) + 2).clamp(0, 19)
+    cc = (torch.arange(24, device=dev).view(1, 24) - 3).clamp(0, 23)
+    assert torch.equal(pkg.interp(I, u), I[:, :, rr, cc])          # integer shift == clamped roll
+
+
+@pytest.mark.parametrize("bcast", ["I", "u"])
+def test_interp_broadcast(pkg, oracle, dev, bcast):
+    I = _rand(1 if bcast == "I" else 4, 2, 24, 20, seed=4)
+    u = 2.0 * _rand(1 if bcast == "u" else 4, 2, 24, 20, seed=5)
+    _check_op(dev, lambda a, b: pkg.interp(a, b), lambda a, b: oracle.interp(a, b), [I, u])
+
+
+@pytest.mark.parametrize("bg", ["clamp", "zero"])
+def test_splat(pkg, oracle, dev, bg):
+    J, u = _rand(3, 2, 32, 28, seed=6), 3.0 * _rand(3, 2, 32, 28, seed=7)
+    conv = oracle.Conventions(background=bg)
+    _check_op(dev, lambda a, b: pkg.splat(a, b, 0.9, False, bg), lambda a, b: oracle.splat(a, b, 0.9, conv=conv), [J, u])
+    out, w = pkg.splat(J.to(dev), u.to(dev), 0.9, True, bg)
+    oc, wc = oracle.splat(J, u, 0.9, need_weights=True, conv=conv)
+    assert relerr(out, oc) < TOL and relerr(w, wc) < TOL
+    # adjointness <interp(I,u), J> == <I, splat(J,u)> on the GPU ops themselves
+    I = _rand(3, 2, 32, 28, seed=8).to(dev)
+    lhs = (pkg.interp(I, u.to(dev), 0.9, bg) * J.to(dev)).double().sum()
+    rhs = (I * out).double().sum()
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+
+
+def test_errors_on_gpu(pkg, dev):
+    with pytest.raises(RuntimeError):
+        pkg.interp(torch.zeros(2, 1, 8, 8, device=dev), torch.zeros(3, 2, 8, 8, device=dev))
+    with pytest.raises(RuntimeError):
+        pkg.interp(torch.zeros(1, 1, 8, 8, device=dev, dtype=torch.float64), torch.zeros(1, 2, 8, 8, device=dev))
+    with pytest.raises(RuntimeError):
+        pkg.FluidMetric(PARAMS).sharp(torch.zeros(1, 2, 48, 48, device=dev))   # not a supported FFT size
+
+
+@pytest.mark.parametrize("disp,tr", [(True, False), (True, True), (False, False), (False, True)])
+def test_jacobian_times_vectorfield(pkg, oracle, dev, disp, tr):
+    v, w = _rand(2, 2, 19, 23, seed=9), _rand(2, 2, 19, 23, seed=10)
+    _check_op(dev, lambda a, b: pkg.jacobian_times_vectorfield(a, b, disp, tr),
+              lambda a, b: oracle.jacobian_times_vectorfield(a, b, disp, tr), [v, w])
+
+
+@pytest.mark.parametrize("bg", ["clamp", "zero"])
+def test_ad_star(pkg, oracle, dev, bg):
+    u, m = 2.0 * _rand(3, 2, 32, 40, seed=11), _rand(3, 2, 32, 40, seed=12)
+    conv = oracle.Conventions(background=bg)
+    _check_op(dev, lambda a, b: pkg.Ad_star(a, b, bg), lambda a, b: oracle.Ad_star(a, b, conv), [u, m])
+
+
+def test_compose(pkg, oracle, dev):
+    u, v = 2.0 * _rand(3, 2, 24, 24, seed=13), 3.0 * _rand(3, 2, 24, 24, seed=14)
+    _check_op(dev, lambda a, b: pkg.compose_disp_vel(a, b, -0.1), lambda a, b: oracle.compose_disp_vel(a, b, -0.1), [u, v])
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (32, 32), (64, 64), (128, 128), (256, 256), (64, 128), (128, 64)])
+@pytest.mark.parametrize("params", [PARAMS, (0.5, 1.0, 0.2)])
+def test_fluid_metric(pkg, oracle, dev, hw, params):
+    H, W = hw
+    P = 5 if H * W <= 128 * 128 else 3
+    f = _rand(P, 2, H, W, seed=15)
+    mg, mc = pkg.FluidMetric(params), oracle.FluidMetric(params)
+    _check_op(dev, mg.flat, mc.flat, [f])
+    _check_op(dev, mg.sharp, mc.sharp, [f])
+    fd = f.to(dev)
+    assert relerr(mg.sharp(mg.flat(fd)), f) < 2e-5                 # sharp(flat(v)) = v
+    const = torch.ones(1, 2, H, W, device=dev) * torch.tensor([2.0, -3.0], device=dev).view(1, 2, 1, 1)
+    assert relerr(mg.flat(const), params[2] * const) < TOL         # flat(const) = gamma*const
+
+
+def test_fluid_many_fields(pkg, oracle, dev):
+    """More fields than resident CTAs: the persistent loop must cover all of them."""
+    f = _rand(700, 2, 32, 32, seed=16)
+    assert relerr(pkg.FluidMetric(PARAMS).sharp(f.to(dev)), oracle.FluidMetric(PARAMS).sharp(f)) < TOL
+
+
+def _smooth_v0(pkg, P, H, W, seed, amp):
+    return pkg.synthetic.synthetic_v0(P, H, W, seed=seed, max_disp=amp)
+
+
+@pytest.mark.parametrize("hw,S", [((32, 32), 4), ((64, 64), 10), ((128, 128), 10), ((64, 128), 3)])
+def test_expmap(pkg, oracle, dev, hw, S):
+    H, W = hw
+    mg, mc = pkg.FluidMetric(PARAMS), oracle.FluidMetric(PARAMS)
+    m0 = mc.flat(_smooth_v0(pkg, 3, H, W, 21, 3.0))
+    u_c = oracle.expmap(mc, m0, num_steps=S)
+    u_g = pkg.expmap(mg, m0.to(dev), num_steps=S)
+    assert relerr(u_g, u_c) < TOL, f"{relerr(u_g, u_c):.2e}"
+    # step-by-step composition of the op-level kernels gives the same geodesic
+    u_s = pkg.expmap(mg, m0.to(dev), num_steps=S, phiinv=torch.zeros_like(m0, device=dev))
+    assert relerr(u_s, u_c) < TOL
+    assert torch.equal(pkg.expmap(mg, torch.zeros(1, 2, H, W, device=dev), num_steps=2), torch.zeros(1, 2, H, W, device=dev))
+
+
+def test_expmap_adjoint(pkg, oracle, dev):
+    """EPDiff adjoint (b2_shoot_bwd) vs autograd through the oracle."""
+    H = W = 32
+    S = 5
+    mg, mc = pkg.FluidMetric(PARAMS), oracle.FluidMetric(PARAMS)
+    m0 = mc.flat(_smooth_v0(pkg, 2, H, W, 22, 2.0))
+    _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S), lambda a: oracle.expmap(mc, a, num_steps=S), [m0],
+              gtol=5e-5)
+    # op-level autograd (EPDiff_step chain) agrees with the fused adjoint
+    _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S, phiinv=torch.zeros_like(a)),
+              lambda a: oracle.expmap(mc, a, num_steps=S), [m0], gtol=5e-5)
+
+
+def _masks(pkg, B, T, H, W, seed=2434):
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W, seed=seed)
+    return pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (128, 128), (256, 256)])
+def test_sector_map_bit_exact(pkg, oracle, dev, hw):
+    H, W = hw
+    src_vol, _ = _masks(pkg, 3, 3, H, W)
+    mask0 = src_vol[:, 0, 0].contiguous()
+    mom = pkg.strain.mask_moments(mask0.to(dev)).cpu()
+    cnt, sx, sy = oracle.mask_moments(mask0)
+    assert torch.equal(mom, torch.stack([cnt, sx, sy], 1))
+    assert torch.equal(pkg.sector_map(mask0.to(dev)).cpu(), oracle.sector_map(mask0))
+    # ragged / degenerate masks: empty, single pixel, full frame
+    odd = torch.zeros(3, H, W)
+    odd[1, 5, 7] = 1
+    odd[2] = 1
+    assert torch.equal(pkg.sector_map(odd.to(dev)).cpu(), oracle.sector_map(odd))
+
+
+@pytest.mark.parametrize("n_frames", [40, 3, None])
+def test_strain_matrix(pkg, oracle, dev, n_frames):
+    B, T, H, W = 2, 6, 64, 64
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    mask0, tar = src_vol[:, 0, 0].contiguous(), tar_vol[:, 0].contiguous()
+    u = _smooth_v0(pkg, B * (T - 1), H, W, 23, 2.5).reshape(B, T - 1, 2, H, W)
+    Sc, cc = oracle.strain_matrix(u, tar, mask0, n_frames=n_frames, return_counts=True)
+    Sg, cg = pkg.strain_matrix(u.to(dev), tar.to(dev), mask0.to(dev), n_frames=n_frames, return_counts=True)
+    assert torch.equal(cg.cpu(), cc)                                   # member counts: bit exact
+    assert relerr(Sg, Sc) < TOL, f"{relerr(Sg, Sc):.2e}"
+    _check_op(dev, lambda a: pkg.strain_matrix(a, tar.to(dev), mask0.to(dev), n_frames=n_frames),
+              lambda a: oracle.strain_matrix(a, tar, mask0, n_frames=n_frames), [u])
+
+
+@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 3), (2, 5, 64, 64, 10), (1, 3, 128, 128, 10), (1, 3, 256, 256, 2)])
+def test_forward_volume_parity(pkg, oracle, dev, cfg):
+    """The fused kernel (and the op-level path for 256^2) vs the oracle, all outputs."""
+    B, T, H, W, S = cfg
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 24, 3.0)
+    ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S)
+    out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S)
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
+        assert out[k].shape == ref[k].shape
+        assert relerr(out[k], ref[k]) < TOL, f"{k}: {relerr(out[k], ref[k]):.2e}"
+
+
+def test_forward_volume_backward(pkg, oracle, dev):
+    """Training-mode gradients through shooting + warp + strain vs autograd through the oracle."""
+    B, T, H, W, S = 2, 4, 32, 32, 4
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 25, 2.0)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=26)
+
+    def loss(out, tarv, sgt):
+        rec = 0.5 * torch.mean((tarv - out["deformed_source"]) ** 2) / 0.03 ** 2 \
+            + 0.1 * (out["velocity"] * out["momentum"]).sum() / tarv.numel()
+        return rec + 1000.0 * torch.mean((out["strain_matrix"] - sgt) ** 2)
+
+    vc = v0.clone().requires_grad_(True)
+    lc = loss(oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S), tar_vol, Sgt)
+    lc.backward()
+    vg = v0.to(dev).requires_grad_(True)
+    lg = loss(pkg.shoot_warp_strain(vg, src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S),
+              tar_vol.to(dev), Sgt.to(dev))
+    lg.backward()
+    assert abs(lg.item() - lc.item()) < 1e-4 * abs(lc.item())
+    assert relerr(vg.grad, vc.grad) < 1e-4, f"{relerr(vg.grad, vc.grad):.2e}"
+
+
+def test_loss_boundary_with_reference_formula(pkg, oracle, dev, golden):
+    """GPU outputs feed the reference's loss formula (registration_losses.py:22-28) unchanged."""
+    B, T, H, W, S = 2, 3, 32, 32, 3
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 27, 2.0)
+    out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S)
+    ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S)
+    lg = oracle.registration_reconstruction_loss({k: v.cpu() for k, v in out.items()}, {"registration_target": tar_vol})
+    lc = oracle.registration_reconstruction_loss(ref, {"registration_target": tar_vol})
+    assert abs(lg - lc) < 1e-5 * abs(lc)
+
+
+def test_models_forward_volume_on_gpu(pkg, dev):
+    """models shim end to end: forward_volume -> LMA net -> backward, keys/shapes of the trainer contract."""
+    torch.manual_seed(2434)
+    B, T, H, W = 2, 5, 64, 64
+    joint = pkg.build_model({"type": "JointRegisterStrainMatNet", "n_strain_matrix_frames": 40,
+                             "strainmat_smoothing_method": "SVD", "strainmat_smoothing_SVD_rank": 5}).to(dev)
+    lma = pkg.build_model({"type": "NetStrainMat2LMA"}).to(dev)
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).to(dev)
+    src_vol, tar_vol = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    pred = joint.forward_volume(src_vol, tar_vol)
+    tos = lma(pred["strain_matrix"])["TOS"]
+    assert pred["strain_matrix"].shape == (B, 1, 126, 40) and tos.shape == (B, 126)
+    assert pred["deformed_source"].shape == tar_vol.shape
+    loss = (pred["deformed_source"] - tar_vol).pow(2).mean() + (pred["velocity"] * pred["momentum"]).sum() * 1e-3 \
+        + pred["strain_matrix"].pow(2).mean() + tos.pow(2).mean()
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in joint.parameters())
+    pair = joint(src_vol[:, :, 0], tar_vol[:, :, 0])
+    assert set(pair) >= {"displacement", "velocity", "momentum", "deformed_source"}
+
+
+def test_full_size_properties(pkg, dev):
+    """BASELINE config-2 size (P=1536, 128^2, S=10): size-independent properties instead of the oracle."""
+    B, T, H, W, S = 64, 25, 128, 128
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    P = B * (T - 1)
+    v0 = _smooth_v0(pkg, P, H, W, 28, 3.0).to(dev)
+    metric = pkg.FluidMetric(PARAMS)
+    out = pkg.shoot_warp_strain(v0, src_vol.to(dev), tar_vol.to(dev), metric, num_steps=S)
+    assert all(torch.isfinite(v).all() for v in out.values())
+    assert relerr(out["velocity"], v0) < 2e-5                     # sharp(flat(v0)) = v0
+    # linearity of flat: momentum(2 v0) = 2 momentum(v0)
+    assert relerr(metric.flat(2 * v0[:64]), 2 * out["momentum"][:64]) < 1e-6
+    # every pair is independent: recomputing a shard alone reproduces the same rows (slice sharding)
+    sub = pkg.shoot_warp_strain(v0[: 4 * (T - 1)], src_vol[:4].to(dev), tar_vol[:4].to(dev), metric, num_steps=S)
+    assert torch.equal(sub["displacement"], out["displacement"][: 4 * (T - 1)])
+    assert torch.equal(sub["deformed_source"], out["deformed_source"][:4])
+    # idempotence / determinism of everything that has no float atomics
+    again = pkg.shoot_warp_strain(v0, src_vol.to(dev), tar_vol.to(dev), metric, num_steps=S)
+    assert torch.equal(again["displacement"], out["displacement"])
+    # warped binary masks stay in [0,1]; zero velocity is the identity map
+    assert out["deformed_source"].min() >= 0 and out["deformed_source"].max() <= 1
+    ident = pkg.shoot_warp_strain(torch.zeros_like(v0[:24]), src_vol[:1].to(dev), tar_vol[:1].to(dev), metric, num_steps=S)
+    assert ident["displacement"].abs().max() == 0
+    assert torch.equal(ident["deformed_source"][0, 0, 0], src_vol[0, 0, 0].to(dev))
+    assert ident["strain_matrix"].abs().max() == 0
