@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py - registered frame-pairs/sec for shoot (S=10 EPDiff steps) + warp + 126-sector strain.
+
+Contract (see the task statement / DESIGN.md section "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[1]: batch of 64 slices x 25 frames, 128x128, per GPU
+(P = 1536 frame-pairs per GPU per step, weak scaling: slices shard across ranks with no
+data-path collective).  A "step" is one pass of the hot path over that batch.
+
+* value    : whole-job frame-pairs/s with inputs resident in HBM (CUDA events, max over ranks)
+* e2e      : same metric through the public API with HOST (pinned) inputs: H2D of v0 + masks and
+             D2H of the strain matrices inside the timed region
+* roofline : algorithmic bytes (700*N per pair) / duration of the fused
+             shooting kernel, against MEASURED_PEAKS.json hbm_gbs
+* cpu_baseline : the torch-CPU oracle (a port: the reference's own lagomorph path is not runnable)
+             on a bounded sample, rank 0, N=1 only
+`--impl reference` times that same CPU oracle with all host threads (the reference's CPU path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "registered frame-pairs/sec (shoot+warp+strain, 128^2)"
+UNIT = "frame-pairs/s"
+B_PER_GPU, T_FRAMES, H, W, S_STEPS = 64, 25, 128, 128, 10
+PARAMS = (1.0, 0.1, 0.05)
+N_SECTORS, N_FRAMES = 126, 40
+BYTES_PER_PAIR = 4 * (15 + 16 * S_STEPS) * H * W          # 700*N at S=10
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-slices", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n_gpus):
+    return {"workload": f"configs[1]: {B_PER_GPU} slices x {T_FRAMES} frames {H}x{W} per GPU, "
+                        f"P={B_PER_GPU * (T_FRAMES - 1)} frame-pairs/GPU/step, EPDiff S={S_STEPS}, "
+                        f"forward shooting + warp + {N_SECTORS}-sector strain",
+            "slices_per_gpu": B_PER_GPU, "frames": T_FRAMES, "grid": [H, W], "epdiff_steps": S_STEPS,
+            "fluid_params": list(PARAMS), "parallelism": f"slice-sharded x{n_gpus}, no data-path collective",
+            "l2_policy": "inputs larger than L2 (v0 201 MB + masks 105 MB per step vs 126 MB L2)"}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (nvidia-smi recipe line)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_inputs(pkg, n_slices, seed):
+    vol = pkg.synthetic.synthetic_masks(n_slices, T_FRAMES, H, W, seed=seed)                  # (B,1,T,H,W)
+    v0 = pkg.synthetic.synthetic_v0(n_slices * (T_FRAMES - 1), H, W, seed=seed + 1, max_disp=3.0)
+    return vol, v0
+
+
+def cpu_pairs_per_s(pkg, n_slices, reps, threads):
+    """The torch-CPU oracle on a bounded sample of the same workload (checker used as baseline only)."""
+    import oracle
+    torch.set_num_threads(threads)
+    vol, v0 = make_inputs(pkg, n_slices, seed=2434)
+    src_vol, tar_vol = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    metric = oracle.FluidMetric(PARAMS)
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            oracle.forward_volume(v0, src_vol, tar_vol, metric, S_STEPS, N_SECTORS, N_FRAMES)
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+    return n_slices * (T_FRAMES - 1) / statistics.median(times), times
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    threads = os.cpu_count() or 1
+    n_slices = args.cpu_sample_slices
+    import oracle
+    torch.set_num_threads(threads)
+    vol, v0 = make_inputs(pkg, n_slices, seed=2434)
+    src_vol, tar_vol = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    metric = oracle.FluidMetric(PARAMS)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            oracle.forward_volume(v0, src_vol, tar_vol, metric, S_STEPS, N_SECTORS, N_FRAMES)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle.forward_volume(v0, src_vol, tar_vol, metric, S_STEPS, N_SECTORS, N_FRAMES)
+        dt = time.perf_counter() - t0
+    pairs = n_slices * (T_FRAMES - 1)
+    value = pairs * args.steps / dt
+    sample = (f"each step = {n_slices} slices x {T_FRAMES - 1} pairs ({pairs} frame-pairs) of the configs[1] workload, "
+              f"torch-CPU fp32 oracle, {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference's own lagomorph CPU path is not runnable (not vendored; SURVEY.md section 0): "
+                    "this is the restated oracle port"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices (the product path has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib, ptr, stream = pkg._lib.lib(), pkg._lib.ptr, pkg._lib.stream
+    metric = pkg.FluidMetric(PARAMS)
+    B, T1 = B_PER_GPU, T_FRAMES - 1
+    P = B * T1
+
+    # ---- inputs: this rank's shard of slices (weak scaling: B_PER_GPU slices per rank)
+    vol_h, v0_h = make_inputs(pkg, B, seed=2434 + 17 * rank)
+    vol_h, v0_h = vol_h.pin_memory(), v0_h.pin_memory()
+    vol_d, v0_d = vol_h.to(dev), v0_h.to(dev)
+    src_vol, tar_vol = pkg.data.split_vol_to_registration_pairs(vol_d, "Lagrangian", 3)
+    tar_vol = tar_vol.contiguous()
+
+    def step_resident():
+        with torch.no_grad():
+            return pkg.shoot_warp_strain(v0_d, src_vol, tar_vol, metric, num_steps=S_STEPS,
+                                         n_sectors=N_SECTORS, n_frames=N_FRAMES)
+
+    S_host = torch.empty((B, 1, N_SECTORS, N_FRAMES), dtype=torch.float32).pin_memory()
+    h2d = vol_h.numel() * 4 + v0_h.numel() * 4
+    d2h = S_host.numel() * 4
+
+    def step_e2e():
+        with torch.no_grad():
+            vd = vol_h.to(dev, non_blocking=True)
+            v0 = v0_h.to(dev, non_blocking=True)
+            sv, tv = pkg.data.split_vol_to_registration_pairs(vd, "Lagrangian", 3)
+            out = pkg.shoot_warp_strain(v0, sv, tv.contiguous(), metric, num_steps=S_STEPS,
+                                        n_sectors=N_SECTORS, n_frames=N_FRAMES)
+            S_host.copy_(out["strain_matrix"], non_blocking=True)
+        return out
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = pkg._lib.launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = pkg._lib.launches() - l0
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # ---- roofline of the dominant kernel: direct C-ABI launches of the fused shooting kernel
+    out = step_resident()
+    mom = pkg.strain.mask_moments(src_vol[:, 0, 0].contiguous())
+    tab = pkg.strain.sector_table(N_SECTORS, dev)
+    a = pkg._lib.ShootArgs()
+    tar_flat = tar_vol.reshape(P, 1, H, W)
+    src0 = src_vol[:, :, 0].contiguous()
+    counts = torch.empty((B, N_SECTORS, T1), dtype=torch.int32, device=dev)
+    a.v0, a.src, a.tar, a.moments, a.table = v0_d.data_ptr(), src0.data_ptr(), tar_flat.data_ptr(), mom.data_ptr(), tab.data_ptr()
+    a.m0, a.vel, a.u = out["momentum"].data_ptr(), out["velocity"].data_ptr(), out["displacement"].data_ptr()
+    a.sdef, a.S, a.counts, a.traj = out["deformed_source"].data_ptr(), out["strain_matrix"].data_ptr(), counts.data_ptr(), None
+    a.B, a.T1, a.H, a.W = B, T1, H, W
+    a.num_steps, a.src_per_pair, a.v0_is_momentum = S_STEPS, 0, 0
+    a.n_sectors, a.n_frames, a.background = N_SECTORS, N_FRAMES, 0
+    a.alpha, a.beta, a.gamma, a.T = PARAMS[0], PARAMS[1], PARAMS[2], 1.0
+    nws = lib.b2_shoot_workspace_bytes(B, T1, H, W, S_STEPS)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    import ctypes
+
+    def kernel_only():
+        pkg._lib.check(lib.b2_shoot_fwd(ctypes.byref(a), ptr(ws), nws, stream()), "b2_shoot_fwd")
+
+    ms_kernel, _ = timed(kernel_only, args.steps, 3)
+    peak, peak_src = peaks()
+    k_ms = ms_kernel / args.steps
+    achieved = P * BYTES_PER_PAIR / (k_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        n = world
+        value = n * P * args.steps / (ms_total * 1e-3)
+        e2e_value = n * P * args.steps / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(n),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "shoot_fwd_kernel<128,128,512> (fused flat + 10 EPDiff steps + warp + strain)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                             "algorithmic_bytes_per_launch": P * BYTES_PER_PAIR,
+                             "note": "op-level algorithmic bytes (700*N per pair); the fused kernel keeps m/v on chip, "
+                                     "so real DRAM traffic is far lower (see profiles/)"}}
+        if n == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cpu_v, cpu_t = cpu_pairs_per_s(pkg, args.cpu_sample_slices, 3, threads)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_sample_slices} slices x {T1} pairs of the same workload, "
+                                              f"torch-CPU fp32 oracle, median of 3 passes"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
