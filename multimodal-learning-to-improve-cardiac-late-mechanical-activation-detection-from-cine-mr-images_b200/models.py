@@ -52,9 +52,12 @@ def svd_smooth(S: torch.Tensor, rank: int) -> torch.Tensor:
     Same operation as ``SVDDenoise`` (/root/reference/modules/data/utils/DENSE_utils.py:11-14),
     selected by ``strainmat_smoothing_method: "SVD"`` (configs/config.json:113-114).
     """
-    U, s, Vh = torch.linalg.svd(S, full_matrices=False)
-    s = torch.cat([s[..., :rank], torch.zeros_like(s[..., rank:])], dim=-1)
-    return (U * s.unsqueeze(-2)) @ Vh
+    # U_r U_r^T S equals the rank-r truncation U_r diag(s_r) V_r^T.  The basis is detached: the strain
+    # matrix is edge-padded beyond the cine frames, hence rank deficient with repeated zero singular
+    # values, where the derivative of the SVD itself is undefined (NaN in torch.linalg.svd backward).
+    with torch.no_grad():
+        U = torch.linalg.svd(S, full_matrices=False)[0][..., :rank]
+    return U @ (U.transpose(-1, -2) @ S)
 
 
 class JointRegisterStrainMatNet(nn.Module):

@@ -203,9 +203,16 @@ def test_forward_volume_parity(pkg, oracle, dev, cfg):
     v0 = _smooth_v0(pkg, B * (T - 1), H, W, 24, 3.0)
     ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S)
     out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S)
+    # float64 run of the same oracle = ground truth: it tells how much of a GPU-vs-fp32-oracle gap is
+    # just fp32 rounding of the oracle itself.  A warped BINARY mask has unit gradient per pixel, so its
+    # error is |du| in pixels (not relative to max|u|): allow what the fp32 oracle itself shows.
+    ref64 = oracle.forward_volume(v0.double(), src_vol.double(), tar_vol.double(), oracle.FluidMetric(PARAMS), S)
     for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
         assert out[k].shape == ref[k].shape
-        assert relerr(out[k], ref[k]) < TOL, f"{k}: {relerr(out[k], ref[k]):.2e}"
+        own = relerr(ref[k], ref64[k])                    # fp32 oracle vs truth
+        tol = TOL if k != "deformed_source" else max(TOL, 3.0 * own)
+        assert relerr(out[k], ref[k]) < tol, f"{k}: {relerr(out[k], ref[k]):.2e} (oracle32 vs 64: {own:.2e})"
+        assert relerr(out[k], ref64[k]) < max(TOL, 2.0 * own), f"{k} vs f64 truth: {relerr(out[k], ref64[k]):.2e}"
 
 
 def test_forward_volume_backward(pkg, oracle, dev):
@@ -266,7 +273,7 @@ def test_models_forward_volume_on_gpu(pkg, dev):
 
 def test_full_size_properties(pkg, dev):
     """BASELINE config-2 size (P=1536, 128^2, S=10): size-independent properties instead of the oracle."""
-    B, T, H, W, S = 64, 25, 128, 128
+    B, T, H, W, S = 64, 25, 128, 128, 10
     src_vol, tar_vol = _masks(pkg, B, T, H, W)
     P = B * (T - 1)
     v0 = _smooth_v0(pkg, P, H, W, 28, 3.0).to(dev)
