@@ -295,4 +295,4 @@ def test_full_size_properties(pkg, dev):
     ident = pkg.shoot_warp_strain(torch.zeros_like(v0[:24]), src_vol[:1].to(dev), tar_vol[:1].to(dev), metric, num_steps=S)
     assert ident["displacement"].abs().max() == 0
     assert torch.equal(ident["deformed_source"][0, 0, 0], src_vol[0, 0, 0].to(dev))
-    assert ident["strain_matrix"].abs().max() == 0
+    assert ident["strain_matrix"].abs().max() < 1e-6               # (|e|^2/|e|^2 - 1)/2 up to fp32 rounding
