@@ -250,6 +250,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches
 
+    # bring the SM clocks out of idle with unrelated work (NOT the hot path): a cold GPU needs tens of
+    # milliseconds to boost, which is longer than W short warm-up steps
+    spin = torch.randn(4096, 4096, device=dev)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.0:
+        spin = (spin @ spin).clamp_(-1, 1)
+        torch.cuda.synchronize()
+    del spin
+
     sampler = ClockSampler(local)
     sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)

@@ -97,10 +97,10 @@ __device__ __forceinline__ void init_twiddles(float2* tw, int tid, int nthreads)
 // FFTs of length N along element stride `es`, for NL lines spaced `ls` apart.
 // Forward (DIR=-1): natural in -> permuted out.  Inverse (DIR=+1): permuted in ->
 // natural out, unnormalised.  Ends with __syncthreads().
-template <int N, int NL, int DIR, int NT>
-__device__ __forceinline__ void fft_lines(float2* __restrict__ z, int es, int ls,
-                                          const float2* __restrict__ tw, int tid) {
+template <int N, int NL, int DIR, int NT, int ES, int LS>
+__device__ __forceinline__ void fft_lines(float2* __restrict__ z, const float2* __restrict__ tw, int tid) {
   constexpr int N1 = Fact<N>::N1, N2 = Fact<N>::N2;
+  constexpr int es = ES, ls = LS;   // compile-time strides: every smem access gets an immediate offset
   if (DIR < 0) {
     for (int t = tid; t < NL * N2; t += NT) {
       const int line = t % NL, n2 = t / NL;
@@ -219,11 +219,11 @@ template <int H, int W, bool INVERSE, int NT>
 __device__ __forceinline__ void fluid_smem(float2* z, const float2* twH, const float2* twW,
                                            const float2* csH, const float2* csW, const FluidParams fp, int tid) {
   constexpr int LD = W + 1;
-  fft_lines<W, H, -1, NT>(z, 1, LD, twW, tid);      // rows: FFT along c, lanes along r
-  fft_lines<H, W, -1, NT>(z, LD, 1, twH, tid);      // cols: FFT along r, lanes along c
+  fft_lines<W, H, -1, NT, 1, LD>(z, twW, tid);      // rows: FFT along c, lanes along r
+  fft_lines<H, W, -1, NT, LD, 1>(z, twH, tid);      // cols: FFT along r, lanes along c
   fluid_multiply<H, W, INVERSE, NT>(z, LD, csH, csW, fp, tid);
-  fft_lines<H, W, +1, NT>(z, LD, 1, twH, tid);
-  fft_lines<W, H, +1, NT>(z, 1, LD, twW, tid);
+  fft_lines<H, W, +1, NT, LD, 1>(z, twH, tid);
+  fft_lines<W, H, +1, NT, 1, LD>(z, twW, tid);
 }
 
 template <int H, int W>

@@ -92,7 +92,7 @@ fft_rows_kernel(const float* __restrict__ f, float2* __restrict__ zg, float* __r
     for (int i = tid; i < RB * W; i += kNTB) z[(i / W) * LD + (i % W)] = zp[i];
   }
   __syncthreads();
-  fft_lines<W, RB, DIR, kNTB>(z, 1, LD, tw, tid);
+  fft_lines<W, RB, DIR, kNTB, 1, LD>(z, tw, tid);
   if (DIR < 0) {
     for (int i = tid; i < RB * W; i += kNTB) zp[i] = z[(i / W) * LD + (i % W)];
   } else {
@@ -128,7 +128,7 @@ fft_cols_kernel(float2* __restrict__ zg, FluidParams fp) {
     z[r * LD + cc] = zp[(size_t)r * W + col];
   }
   __syncthreads();
-  fft_lines<H, NC, -1, kNTB>(z, LD, 1, tw, tid);
+  fft_lines<H, NC, -1, kNTB, LD, 1>(z, tw, tid);
   for (int t = tid; t < H * N2w; t += kNTB) {
     const int pr = t / N2w, cc = t % N2w, pc = j * N2w + cc;
     const int k0 = cell_to_freq<H>(pr), k1 = cell_to_freq<W>(pc);
@@ -145,7 +145,7 @@ fft_cols_kernel(float2* __restrict__ zg, FluidParams fp) {
       z[qr * LD + qcc] = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
   }
   __syncthreads();
-  fft_lines<H, NC, +1, kNTB>(z, LD, 1, tw, tid);
+  fft_lines<H, NC, +1, kNTB, LD, 1>(z, tw, tid);
   const int ncols = self ? N2w : NC;
   for (int i = tid; i < H * NC; i += kNTB) {
     const int r = i / NC, cc = i % NC;

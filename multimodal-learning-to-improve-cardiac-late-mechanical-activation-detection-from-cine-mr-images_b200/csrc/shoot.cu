@@ -16,6 +16,8 @@
 //
 // Path B (256x256 / rectangular): the same algorithm as a sequence of the
 // op-level kernels (HBM-bound per op).
+#include <stdlib.h>
+
 #include "fft.cuh"
 #include "strain.cuh"
 
@@ -192,6 +194,16 @@ static int sm_count() {
   return sms;
 }
 
+// threads per CTA of the 128x128 kernel (tuning knob; B2_SHOOT_NT=512|1024 overrides for A/B runs)
+static int nt128() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("B2_SHOOT_NT");
+    v = (e && atoi(e) == 512) ? 512 : 1024;   // 1024 measured 22 % faster (profiles/r01_b)
+  }
+  return v;
+}
+
 static bool fused_size(int64_t H, int64_t W) { return H == W && (H == 16 || H == 32 || H == 64 || H == 128); }
 
 static int64_t fused_grid(int64_t P, int64_t H) {
@@ -200,7 +212,7 @@ static int64_t fused_grid(int64_t P, int64_t H) {
     case 16: per = FusedCfg<16, 16, 128>::ctas_per_sm(); break;
     case 32: per = FusedCfg<32, 32, 256>::ctas_per_sm(); break;
     case 64: per = FusedCfg<64, 64, 256>::ctas_per_sm(); break;
-    case 128: per = FusedCfg<128, 128, 512>::ctas_per_sm(); break;
+    case 128: per = 1; break;
   }
   int64_t g = (int64_t)sm_count() * per;
   return g < P ? g : P;
@@ -275,7 +287,8 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
       case 16: return launch_fused<16, 16, 128>(prm, grid, st);
       case 32: return launch_fused<32, 32, 256>(prm, grid, st);
       case 64: return launch_fused<64, 64, 256>(prm, grid, st);
-      case 128: return launch_fused<128, 128, 512>(prm, grid, st);
+      case 128: return nt128() == 1024 ? launch_fused<128, 128, 1024>(prm, grid, st)
+                                       : launch_fused<128, 128, 512>(prm, grid, st);
     }
     return B2_E_FFTSIZE;
   }
