@@ -191,25 +191,43 @@ __device__ __forceinline__ void fluid_coeffs(const FluidParams& fp, float2 cs0, 
   Bi = fp.scale * b;
 }
 
-// In-place multiplier on the permuted 2-D spectrum z[r*LD + c]; each thread owns a
-// cell and its mirror (-k0, -k1) and writes both.  Ends with __syncthreads().
+// In-place multiplier on the permuted 2-D spectrum z[r*(W+1) + c].  Work is enumerated over the
+// canonical half of the row frequencies k0 in [0, H/2]: a thread owns cell (k0, pc) AND its mirror
+// (-k0, -k1) and writes both, so nobody idles on a "not my pair" test.  The thread's column (pc), its
+// mirror column and the column part of the symbol are loop invariant (NT is a multiple of W); the row
+// part is warp uniform.  Ends with __syncthreads().
 template <int H, int W, bool INVERSE, int NT>
-__device__ __forceinline__ void fluid_multiply(float2* __restrict__ z, int LD, const float2* __restrict__ csH,
+__device__ __forceinline__ void fluid_multiply(float2* __restrict__ z, const float2* __restrict__ csH,
                                                const float2* __restrict__ csW, const FluidParams fp, int tid) {
-  for (int t = tid; t < H * W; t += NT) {
-    const int pr = t / W, pc = t % W;
-    const int k0 = cell_to_freq<H>(pr), k1 = cell_to_freq<W>(pc);
-    const int qr = freq_to_cell<H>((H - k0) & (H - 1)), qc = freq_to_cell<W>((W - k1) & (W - 1));
-    const int lin = pr * W + pc, linq = qr * W + qc;
-    if (lin > linq) continue;
+  static_assert(NT % W == 0, "threads per CTA must be a multiple of the row length");
+  constexpr int LD = W + 1, RB = NT / W;
+  const int pc = tid % W, br = tid / W;
+  const int k1 = cell_to_freq<W>(pc);
+  const int qc = freq_to_cell<W>((W - k1) & (W - 1));
+  const float2 cs1 = csW[k1];
+  const float h = 0.5f * fp.scale;
+  const float bs1 = fp.beta * cs1.y;
+  for (int k0 = br; k0 <= H / 2; k0 += RB) {
+    const int pr = freq_to_cell<H>(k0), qr = freq_to_cell<H>((H - k0) & (H - 1));
+    if (pr == qr && pc > qc) continue;          // self-mirrored rows (k0 = 0, H/2): each pair once
+    const float2 cs0 = csH[k0];
+    const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
+    const float L00 = lam + fp.beta * cs0.x;
+    const float L11 = lam + fp.beta * cs1.x;
+    const float L01 = cs0.y * bs1;
     float A, Br, Bi;
-    fluid_coeffs<INVERSE>(fp, csH[k0], csW[k1], A, Br, Bi);
-    const float2 Z = z[pr * LD + pc];
-    const float2 Zq = z[qr * LD + qc];
+    if (INVERSE) {
+      const float idet = __fdividef(h, L00 * L11 - L01 * L01);
+      A = idet * (L11 + L00); Br = idet * (L11 - L00); Bi = -2.0f * idet * L01;
+    } else {
+      A = h * (L00 + L11); Br = h * (L00 - L11); Bi = 2.0f * h * L01;
+    }
+    float2* zp = z + pr * LD + pc;
+    float2* zq = z + qr * LD + qc;
+    const float2 Z = *zp, Zq = *zq;
     // W(k) = A Z + B conj(Zq);  W(-k) = A Zq + B conj(Z)
-    z[pr * LD + pc] = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
-    if (lin != linq)
-      z[qr * LD + qc] = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
+    *zp = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
+    if (zp != zq) *zq = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
   }
   __syncthreads();
 }
@@ -221,7 +239,7 @@ __device__ __forceinline__ void fluid_smem(float2* z, const float2* twH, const f
   constexpr int LD = W + 1;
   fft_lines<W, H, -1, NT, 1, LD>(z, twW, tid);      // rows: FFT along c, lanes along r
   fft_lines<H, W, -1, NT, LD, 1>(z, twH, tid);      // cols: FFT along r, lanes along c
-  fluid_multiply<H, W, INVERSE, NT>(z, LD, csH, csW, fp, tid);
+  fluid_multiply<H, W, INVERSE, NT>(z, csH, csW, fp, tid);
   fft_lines<H, W, +1, NT, LD, 1>(z, twH, tid);
   fft_lines<W, H, +1, NT, 1, LD>(z, twW, tid);
 }

@@ -44,12 +44,16 @@ struct ShootSmem {
   static constexpr size_t bytes = bins_off + sizeof(int32_t) * 4 * kFusedMaxSectors;
 };
 
+// Thread <-> pixel map of every per-pixel phase: a thread keeps ONE column c = tid % W and walks the
+// rows r = tid / W, + RB, + 2 RB ... (RB = NT / W rows per band), so lanes run along the contiguous axis
+// (coalesced global rows, conflict-free smem rows) and all addresses advance by constants.
 template <int H, int W, int NT, int BG>
 __global__ void __launch_bounds__(NT)
 shoot_fwd_kernel(const ShootParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using FS = FluidSmem<H, W>;
-  constexpr int LD = FS::LD, N = H * W;
+  static_assert(NT % W == 0 && H % (NT / W) == 0, "CTA must tile the grid in whole row bands");
+  constexpr int LD = FS::LD, N = H * W, RB = NT / W, NB = H / RB;
   float2 *z, *twH, *twW, *csH, *csW;
   FS::carve(smem_raw, z, twH, twW, csH, csW);
   int32_t* tab_s = reinterpret_cast<int32_t*>(smem_raw + ShootSmem<H, W>::bins_off);
@@ -58,10 +62,13 @@ shoot_fwd_kernel(const ShootParams prm) {
   float* sums_s = reinterpret_cast<float*>(tab_s + 2 * n_sectors);
   int* cnts_s = tab_s + 3 * n_sectors;
   const int tid = threadIdx.x;
+  const int c = tid % W, br = tid / W;
   const int S = a.num_steps;
   const float dt = a.T / (float)S, mdt = -dt;
   const FluidParams fp{a.alpha, a.beta, a.gamma, 1.0f / (float)N};
   const int64_t P = prm.P;
+  const int cl = max(c - 1, 0), cr = min(c + 1, W - 1);
+  const float sc = (c == 0 || c == W - 1) ? 1.f : 0.5f;
 
   FS::init_luts(twH, twW, csH, csW, tid, NT);
   if (a.S)
@@ -79,7 +86,11 @@ shoot_fwd_kernel(const ShootParams prm) {
     // ---- m0 = flat(v0)   (or m0 given directly: lagomorph.expmap(metric, m0))
     {
       const float* f0 = a.v0 + (size_t)p * prm.field;
-      for (int i = tid; i < N; i += NT) z[(i / W) * LD + (i % W)] = make_float2(__ldg(f0 + i), __ldg(f0 + N + i));
+#pragma unroll 4
+      for (int k = 0; k < NB; ++k) {
+        const int r = k * RB + br;
+        z[r * LD + c] = make_float2(__ldg(f0 + r * W + c), __ldg(f0 + N + r * W + c));
+      }
     }
     __syncthreads();
     if (a.v0_is_momentum) {
@@ -87,82 +98,102 @@ shoot_fwd_kernel(const ShootParams prm) {
     } else {
       float* m0w = a.m0 ? a.m0 + (size_t)p * prm.field : scr_m;
       fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
-      for (int i = tid; i < N; i += NT) {
-        const float2 v = z[(i / W) * LD + (i % W)];
-        m0w[i] = v.x;
-        m0w[N + i] = v.y;
+#pragma unroll 4
+      for (int k = 0; k < NB; ++k) {
+        const int r = k * RB + br;
+        const float2 v = z[r * LD + c];
+        m0w[r * W + c] = v.x;
+        m0w[N + r * W + c] = v.y;
       }
       m0g = m0w;
       __syncthreads();   // every thread has read z before the next transform overwrites it
     }
 
-    const float* ucur = nullptr;   // u_s (nullptr == identically zero)
+    const float* ucur = nullptr;   // u_s in global memory (nullptr == identically zero)
     for (int s = 0; s < S; ++s) {
-      // ---- m = Ad*_{u_s} m0  -> z
+      // ---- m = Ad*_{u_s} m0 -> z.  z holds u_s (float2 per pixel, written by the previous compose):
+      // the (I + Du)^T stencil reads shared memory; only the 4-tap gather of m0 goes to L1/L2.
+      // Band k is overwritten with m only after every thread has read it (one barrier per band); the
+      // row above the next band is prefetched into a register before it is overwritten.
       if (s > 0) {
-        __syncthreads();   // m0g / u_s stores visible; previous readers of z done
-        const float* u0 = ucur;
-        const float* u1 = ucur + N;
-        for (int i = tid; i < N; i += NT) {
-          const int r = i / W, c = i % W;
-          int rlo, rhi, clo, chi; float sr, sc;
-          diff_idx(r, H, rlo, rhi, sr);
-          diff_idx(c, W, clo, chi, sc);
-          const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
-          const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
-          const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
-          const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
-          const Taps tp = make_taps<BG>((float)r + u0[i], (float)c + u1[i], H, W);
+        float2 up_saved = make_float2(0.f, 0.f);
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br;
+          const float2 ce = z[r * LD + c];
+          const float2 up = (br == 0) ? (k == 0 ? ce : up_saved) : z[(r - 1) * LD + c];
+          const float2 dn = (r == H - 1) ? ce : z[(r + 1) * LD + c];
+          const float2 lf = z[r * LD + cl];
+          const float2 rt = z[r * LD + cr];
+          float2 up_next = up_saved;
+          if (br == 0 && k + 1 < NB) up_next = z[((k + 1) * RB - 1) * LD + c];
+          const float sr = (r == 0 || r == H - 1) ? 1.f : 0.5f;
+          const float d00 = sr * (dn.x - up.x), d10 = sr * (dn.y - up.y);
+          const float d01 = sc * (rt.x - lf.x), d11 = sc * (rt.y - lf.y);
+          const Taps tp = make_taps<BG>((float)r + ce.x, (float)c + ce.y, H, W);
           const float w0 = tap_sample<BG>(tp, m0g[tp.o00], m0g[tp.o10], m0g[tp.o01], m0g[tp.o11]);
           const float w1 = tap_sample<BG>(tp, m0g[N + tp.o00], m0g[N + tp.o10], m0g[N + tp.o01], m0g[N + tp.o11]);
-          z[r * LD + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+          const float2 m = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+          __syncthreads();
+          z[r * LD + c] = m;
+          up_saved = up_next;
         }
         __syncthreads();
       }
       // ---- v = sharp(m)  (in shared memory)
       fluid_smem<H, W, true, NT>(z, twH, twW, csH, csW, fp, tid);
 
-      // ---- u_{s+1} = interp(u_s, v, -dt) - dt v ; trajectory / velocity outputs
+      // ---- u_{s+1} = interp(u_s, v, -dt) - dt v  -> global (gathers of the next step, outputs) and,
+      // in place of v, into z (stencil of the next Ad*); trajectory / velocity outputs
       float* unext;
       if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * P + p) * prm.field : uout;
       else unext = (((S - (s + 1)) & 1) == 0) ? uout : scr_u;
       float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * P + p) * prm.field : nullptr;
-      float* utraj0 = (a.traj && s == 0) ? a.traj + ((size_t)p) * prm.field : nullptr;
-      float* velout = (s == 0 && a.vel) ? a.vel + (size_t)p * prm.field : nullptr;
-      for (int i = tid; i < N; i += NT) {
-        const int r = i / W, c = i % W;
-        const float2 v = z[r * LD + c];
-        float n0, n1;
-        if (s == 0) {
-          n0 = mdt * v.x;
-          n1 = mdt * v.y;
+      if (s == 0) {
+        float* utraj0 = a.traj ? a.traj + ((size_t)p) * prm.field : nullptr;
+        float* velout = a.vel ? a.vel + (size_t)p * prm.field : nullptr;
+#pragma unroll 2
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          const float2 v = z[r * LD + c];
+          const float2 n = make_float2(mdt * v.x, mdt * v.y);
+          unext[i] = n.x;
+          unext[N + i] = n.y;
+          z[r * LD + c] = n;
           if (utraj0) { utraj0[i] = 0.f; utraj0[N + i] = 0.f; }
           if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
-        } else {
-          const float* u0 = ucur;
-          const float* u1 = ucur + N;
-          const Taps tp = make_taps<BG>((float)r + mdt * v.x, (float)c + mdt * v.y, H, W);
-          n0 = tap_sample<BG>(tp, u0[tp.o00], u0[tp.o10], u0[tp.o01], u0[tp.o11]) + mdt * v.x;
-          n1 = tap_sample<BG>(tp, u1[tp.o00], u1[tp.o10], u1[tp.o01], u1[tp.o11]) + mdt * v.y;
+          if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
         }
-        unext[i] = n0;
-        unext[N + i] = n1;
-        if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+      } else {
+        const float* u0 = ucur;
+        const float* u1 = ucur + N;
+#pragma unroll 2
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          const float2 v = z[r * LD + c];
+          const Taps tp = make_taps<BG>((float)r + mdt * v.x, (float)c + mdt * v.y, H, W);
+          float2 n;
+          n.x = tap_sample<BG>(tp, u0[tp.o00], u0[tp.o10], u0[tp.o01], u0[tp.o11]) + mdt * v.x;
+          n.y = tap_sample<BG>(tp, u1[tp.o00], u1[tp.o10], u1[tp.o01], u1[tp.o11]) + mdt * v.y;
+          unext[i] = n.x;
+          unext[N + i] = n.y;
+          z[r * LD + c] = n;
+          if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+        }
       }
       ucur = unext;
+      __syncthreads();   // u_{s+1} visible to the whole CTA (global and shared copies)
     }
-    __syncthreads();   // u^S visible to the whole CTA
 
     // ---- deformed_source = interp(src, u^S)
     if (a.sdef) {
       const float* src = a.src + (size_t)(a.src_per_pair ? p : b) * N;
       float* sd = a.sdef + (size_t)p * N;
-      const float* u0 = ucur;
-      const float* u1 = ucur + N;
-      for (int i = tid; i < N; i += NT) {
-        const int r = i / W, c = i % W;
-        const Taps tp = make_taps<BG>((float)r + u0[i], (float)c + u1[i], H, W);
-        sd[i] = tap_sample<BG>(tp, __ldg(src + tp.o00), __ldg(src + tp.o10), __ldg(src + tp.o01), __ldg(src + tp.o11));
+#pragma unroll 2
+      for (int k = 0; k < NB; ++k) {
+        const int r = k * RB + br;
+        const float2 u = z[r * LD + c];
+        const Taps tp = make_taps<BG>((float)r + u.x, (float)c + u.y, H, W);
+        sd[r * W + c] = tap_sample<BG>(tp, __ldg(src + tp.o00), __ldg(src + tp.o10), __ldg(src + tp.o01), __ldg(src + tp.o11));
       }
     }
     // ---- strain matrix column t of slice b
