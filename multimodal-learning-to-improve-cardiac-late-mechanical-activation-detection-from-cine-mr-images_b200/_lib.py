@@ -10,7 +10,10 @@ import pathlib
 
 import torch
 
-_LIB_PATH = pathlib.Path(__file__).resolve().parent / "libb2lddmm.so"
+import os
+
+# B2LDDMM_LIB selects an alternative build of the same C ABI (A/B tuning runs only)
+_LIB_PATH = pathlib.Path(os.environ.get("B2LDDMM_LIB") or pathlib.Path(__file__).resolve().parent / "libb2lddmm.so")
 _lib = None
 
 c_f = C.c_void_p       # float* / any device pointer

@@ -74,6 +74,45 @@ __device__ __forceinline__ void tap_grad(const Taps& t, float v00, float v10, fl
   g1 = (1.f - t.a) * (v01 - v00) + t.a * (v11 - v10);
 }
 
+// Bilinear samples of the two planes f, f+plane at (p0,p1).  Warp-uniform fast path: when every lane's
+// 2x2 footprint lies inside the image, the four taps are base + {0, 1, W, W+1} (immediate offsets from ONE
+// address, no clamps); otherwise the whole warp takes the background-ruled path.  Both paths use the same
+// weights and tap values, so results are bit-identical.  All 32 lanes must call this converged.
+template <int BG, bool FAST = true>
+__device__ __forceinline__ void gather2(const float* f, int plane, float p0, float p1, int H, int W,
+                                        float& w0, float& w1) {
+  const float f0 = floorf(p0), f1 = floorf(p1);
+  const int i0 = (int)f0, j0 = (int)f1;            // cvt saturates, NaN -> 0: the slow path handles those
+  const bool interior = ((unsigned)i0 < (unsigned)(H - 1)) & ((unsigned)j0 < (unsigned)(W - 1));
+  if (FAST && __all_sync(0xffffffffu, interior)) {
+    const float a = p0 - f0, b = p1 - f1, oma = 1.f - a, omb = 1.f - b;
+    const float* q = f + i0 * W + j0;
+    const float c00 = oma * omb, c01 = oma * b, c10 = a * omb, c11 = a * b;
+    w0 = ((c00 * q[0] + c01 * q[1]) + c10 * q[W]) + c11 * q[W + 1];
+    q += plane;
+    w1 = ((c00 * q[0] + c01 * q[1]) + c10 * q[W]) + c11 * q[W + 1];
+  } else {
+    const Taps t = make_taps<BG>(p0, p1, H, W);
+    w0 = tap_sample<BG>(t, f[t.o00], f[t.o10], f[t.o01], f[t.o11]);
+    f += plane;
+    w1 = tap_sample<BG>(t, f[t.o00], f[t.o10], f[t.o01], f[t.o11]);
+  }
+}
+
+template <int BG>
+__device__ __forceinline__ float gather1_ldg(const float* __restrict__ f, float p0, float p1, int H, int W) {
+  const float f0 = floorf(p0), f1 = floorf(p1);
+  const int i0 = (int)f0, j0 = (int)f1;
+  const bool interior = ((unsigned)i0 < (unsigned)(H - 1)) & ((unsigned)j0 < (unsigned)(W - 1));
+  if (__all_sync(0xffffffffu, interior)) {
+    const float a = p0 - f0, b = p1 - f1, oma = 1.f - a, omb = 1.f - b;
+    const float* q = f + i0 * W + j0;
+    return (((oma * omb) * __ldg(q) + (oma * b) * __ldg(q + 1)) + (a * omb) * __ldg(q + W)) + (a * b) * __ldg(q + W + 1);
+  }
+  const Taps t = make_taps<BG>(p0, p1, H, W);
+  return tap_sample<BG>(t, __ldg(f + t.o00), __ldg(f + t.o10), __ldg(f + t.o01), __ldg(f + t.o11));
+}
+
 // ---------------------------------------------------------------------------
 // Finite differences (A.3): central inside, one-sided at the first/last index.
 // ---------------------------------------------------------------------------

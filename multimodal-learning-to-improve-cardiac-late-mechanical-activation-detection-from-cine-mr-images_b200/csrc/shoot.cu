@@ -29,6 +29,10 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
                     int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st);
 
 constexpr int kFusedMaxSectors = 256;
+#ifndef B2_FAST_GATHER
+#define B2_FAST_GATHER 0
+#endif
+constexpr bool kFastGather = B2_FAST_GATHER != 0;
 
 struct ShootParams {
   b2_shoot_args a;
@@ -116,25 +120,30 @@ shoot_fwd_kernel(const ShootParams prm) {
       // Band k is overwritten with m only after every thread has read it (one barrier per band); the
       // row above the next band is prefetched into a register before it is overwritten.
       if (s > 0) {
+        constexpr int G = NB < 4 ? NB : 4;       // bands per barrier: G pixels of m stay in registers
         float2 up_saved = make_float2(0.f, 0.f);
-        for (int k = 0; k < NB; ++k) {
-          const int r = k * RB + br;
-          const float2 ce = z[r * LD + c];
-          const float2 up = (br == 0) ? (k == 0 ? ce : up_saved) : z[(r - 1) * LD + c];
-          const float2 dn = (r == H - 1) ? ce : z[(r + 1) * LD + c];
-          const float2 lf = z[r * LD + cl];
-          const float2 rt = z[r * LD + cr];
+        for (int g = 0; g < NB / G; ++g) {
+          float2 m[G];
           float2 up_next = up_saved;
-          if (br == 0 && k + 1 < NB) up_next = z[((k + 1) * RB - 1) * LD + c];
-          const float sr = (r == 0 || r == H - 1) ? 1.f : 0.5f;
-          const float d00 = sr * (dn.x - up.x), d10 = sr * (dn.y - up.y);
-          const float d01 = sc * (rt.x - lf.x), d11 = sc * (rt.y - lf.y);
-          const Taps tp = make_taps<BG>((float)r + ce.x, (float)c + ce.y, H, W);
-          const float w0 = tap_sample<BG>(tp, m0g[tp.o00], m0g[tp.o10], m0g[tp.o01], m0g[tp.o11]);
-          const float w1 = tap_sample<BG>(tp, m0g[N + tp.o00], m0g[N + tp.o10], m0g[N + tp.o01], m0g[N + tp.o11]);
-          const float2 m = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
-          __syncthreads();
-          z[r * LD + c] = m;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int k = g * G + j, r = k * RB + br;
+            const float2 ce = z[r * LD + c];
+            const float2 up = (br == 0) ? (j == 0 ? (g == 0 ? ce : up_saved) : z[(r - 1) * LD + c]) : z[(r - 1) * LD + c];
+            const float2 dn = (r == H - 1) ? ce : z[(r + 1) * LD + c];
+            const float2 lf = z[r * LD + cl];
+            const float2 rt = z[r * LD + cr];
+            if (j == G - 1 && br == 0 && g + 1 < NB / G) up_next = z[((k + 1) * RB - 1) * LD + c];
+            const float sr = (r == 0 || r == H - 1) ? 1.f : 0.5f;
+            const float d00 = sr * (dn.x - up.x), d10 = sr * (dn.y - up.y);
+            const float d01 = sc * (rt.x - lf.x), d11 = sc * (rt.y - lf.y);
+            float w0, w1;
+            gather2<BG, kFastGather>(m0g, N, (float)r + ce.x, (float)c + ce.y, H, W, w0, w1);
+            m[j] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+          }
+          __syncthreads();                       // every thread has read the rows of this group
+#pragma unroll
+          for (int j = 0; j < G; ++j) z[((g * G + j) * RB + br) * LD + c] = m[j];
           up_saved = up_next;
         }
         __syncthreads();
@@ -164,16 +173,14 @@ shoot_fwd_kernel(const ShootParams prm) {
           if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
         }
       } else {
-        const float* u0 = ucur;
-        const float* u1 = ucur + N;
 #pragma unroll 2
         for (int k = 0; k < NB; ++k) {
           const int r = k * RB + br, i = r * W + c;
           const float2 v = z[r * LD + c];
-          const Taps tp = make_taps<BG>((float)r + mdt * v.x, (float)c + mdt * v.y, H, W);
           float2 n;
-          n.x = tap_sample<BG>(tp, u0[tp.o00], u0[tp.o10], u0[tp.o01], u0[tp.o11]) + mdt * v.x;
-          n.y = tap_sample<BG>(tp, u1[tp.o00], u1[tp.o10], u1[tp.o01], u1[tp.o11]) + mdt * v.y;
+          gather2<BG, kFastGather>(ucur, N, (float)r + mdt * v.x, (float)c + mdt * v.y, H, W, n.x, n.y);
+          n.x += mdt * v.x;
+          n.y += mdt * v.y;
           unext[i] = n.x;
           unext[N + i] = n.y;
           z[r * LD + c] = n;
@@ -192,8 +199,7 @@ shoot_fwd_kernel(const ShootParams prm) {
       for (int k = 0; k < NB; ++k) {
         const int r = k * RB + br;
         const float2 u = z[r * LD + c];
-        const Taps tp = make_taps<BG>((float)r + u.x, (float)c + u.y, H, W);
-        sd[r * W + c] = tap_sample<BG>(tp, __ldg(src + tp.o00), __ldg(src + tp.o10), __ldg(src + tp.o01), __ldg(src + tp.o11));
+        sd[r * W + c] = gather1_ldg<BG>(src, (float)r + u.x, (float)c + u.y, H, W);
       }
     }
     // ---- strain matrix column t of slice b
