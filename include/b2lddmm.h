@@ -152,6 +152,10 @@ typedef struct b2_shoot_args {
   int32_t* counts;
   float* traj;
   int64_t B, T1, H, W;
+  int64_t src_slice_stride;  /* elements between the source images of consecutive slices; 0 = H*W */
+  int64_t tar_slice_stride;  /* elements between the first target frames of consecutive slices; 0 = T1*H*W.
+                                With both set to T*H*W, src = vol and tar = vol + H*W read a (B,1,T,H,W) cine
+                                volume in place: no pair construction, no copies (fused path only). */
   int32_t num_steps;
   int32_t src_per_pair;
   int32_t v0_is_momentum;  /* != 0: `v0` already holds m0 (lagomorph.expmap(metric, m0)); flat is skipped,

@@ -16,7 +16,7 @@ from .ops import (  # noqa: F401
     jacobian_times_vectorfield,
     splat,
 )
-from .shooting import EPDiff_step, expmap, shoot_warp_pairs, shoot_warp_strain  # noqa: F401
+from .shooting import EPDiff_step, HostPipeline, expmap, shoot_warp_pairs, shoot_warp_strain  # noqa: F401
 from .strain import sector_map, strain_matrix  # noqa: F401
 
 __version__ = "0.1.0"

@@ -30,6 +30,7 @@ class ShootArgs(C.Structure):
         ("m0", C.c_void_p), ("vel", C.c_void_p), ("u", C.c_void_p), ("sdef", C.c_void_p),
         ("S", C.c_void_p), ("counts", C.c_void_p), ("traj", C.c_void_p),
         ("B", C.c_int64), ("T1", C.c_int64), ("H", C.c_int64), ("W", C.c_int64),
+        ("src_slice_stride", C.c_int64), ("tar_slice_stride", C.c_int64),
         ("num_steps", C.c_int32), ("src_per_pair", C.c_int32), ("v0_is_momentum", C.c_int32),
         ("n_sectors", C.c_int32), ("n_frames", C.c_int32), ("background", C.c_int32),
         ("alpha", C.c_float), ("beta", C.c_float), ("gamma", C.c_float), ("T", C.c_float),

@@ -193,7 +193,8 @@ shoot_fwd_kernel(const ShootParams prm) {
 
     // ---- deformed_source = interp(src, u^S)
     if (a.sdef) {
-      const float* src = a.src + (size_t)(a.src_per_pair ? p : b) * N;
+      const float* src = a.src_per_pair ? a.src + (size_t)p * N
+                                        : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
       float* sd = a.sdef + (size_t)p * N;
 #pragma unroll 2
       for (int k = 0; k < NB; ++k) {
@@ -206,7 +207,9 @@ shoot_fwd_kernel(const ShootParams prm) {
     if (a.S) {
       for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0.f; cnts_s[i] = 0; }
       __syncthreads();
-      strain_bin_frame<NT>(ucur, ucur + N, a.tar + (size_t)p * N, reinterpret_cast<const long long*>(a.moments) + 3 * b,
+      const float* tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N
+                                             : a.tar + (size_t)p * N;
+      strain_bin_frame<NT>(ucur, ucur + N, tarp, reinterpret_cast<const long long*>(a.moments) + 3 * b,
                            tab_s, n_sectors, H, W, sums_s, cnts_s, tid);
       strain_store_column<NT>(sums_s, cnts_s, a.S, a.counts, (int)b, t, (int)a.T1, n_sectors, a.n_frames, tid);
     }
@@ -331,6 +334,7 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   }
 
   // ---- path B: op-level sequence
+  if (a.src_slice_stride || a.tar_slice_stride) return B2_E_PARAM;   // strided volumes: fused path only
   if (b2_fluid_workspace_bytes(P, H, W) <= 0) return B2_E_FFTSIZE;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   const size_t fbytes = align256(sizeof(float) * (size_t)P * field);

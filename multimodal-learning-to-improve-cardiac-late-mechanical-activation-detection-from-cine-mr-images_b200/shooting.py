@@ -33,11 +33,7 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
 
-def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background, n_sectors, n_frames,
-                  B, T1, want, v0_is_momentum, src_per_pair, save_traj):
-    """Allocate outputs and run ``b2_shoot_fwd``.  ``want`` selects optional outputs."""
-    P, _, H, W = v0.shape
-    dev = v0.device
+def _alloc_outputs(P, B, T1, H, W, dev, want, v0_is_momentum, n_sectors, n_frames, num_steps, save_traj):
     new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
     out = {"u": new(P, 2, H, W)}
     if want.get("m0") and not v0_is_momentum:
@@ -51,6 +47,17 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
         out["counts"] = torch.empty((B, n_sectors, T1), dtype=torch.int32, device=dev)
     if save_traj:
         out["traj"] = new(num_steps, 2, P, 2, H, W)
+    return out
+
+
+def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background, n_sectors, n_frames,
+                  B, T1, want, v0_is_momentum, src_per_pair, save_traj, out=None, ws=None,
+                  src_slice_stride=0, tar_slice_stride=0):
+    """Run ``b2_shoot_fwd``; outputs are allocated here unless ``out`` (contiguous tensors) is given."""
+    P, _, H, W = v0.shape
+    dev = v0.device
+    if out is None:
+        out = _alloc_outputs(P, B, T1, H, W, dev, want, v0_is_momentum, n_sectors, n_frames, num_steps, save_traj)
     a = ShootArgs()
     a.v0, a.src, a.tar = v0.data_ptr(), (src.data_ptr() if src is not None else None), \
         (tar.data_ptr() if tar is not None else None)
@@ -59,13 +66,15 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
     for k in ("m0", "vel", "u", "sdef", "S", "counts", "traj"):
         setattr(a, k, out[k].data_ptr() if k in out else None)
     a.B, a.T1, a.H, a.W = B, T1, H, W
+    a.src_slice_stride, a.tar_slice_stride = int(src_slice_stride), int(tar_slice_stride)
     a.num_steps, a.src_per_pair, a.v0_is_momentum = int(num_steps), int(src_per_pair), int(v0_is_momentum)
     a.n_sectors, a.n_frames, a.background = int(n_sectors), int(n_frames), int(background)
     a.alpha, a.beta, a.gamma, a.T = metric.alpha, metric.beta, metric.gamma, float(T)
     nbytes = lib().b2_shoot_workspace_bytes(B, T1, H, W, int(num_steps))
     if nbytes <= 0:
         check(-4, "b2_shoot_workspace_bytes")
-    ws = _workspace(nbytes, dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = _workspace(nbytes, dev)
     check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), nbytes, stream()), "b2_shoot_fwd")
     fused = (H == W and H in (16, 32, 64, 128))
     _lib.count_launch(1 if fused else 3 + 5 * int(num_steps) + 2)
@@ -129,19 +138,23 @@ def expmap(metric: FluidMetric, m0, T=1.0, num_steps=10, phiinv=None, mommask=No
 
 
 class ShootWarpStrainFunction(torch.autograd.Function):
-    """(v0, src, tar) -> (m0, vel, u, sdef, S): the body of ``forward_volume`` as one kernel."""
+    """(v0, src, tar) -> (m0, vel, u, sdef, S): the body of ``forward_volume`` as one kernel.
+
+    ``src`` / ``tar`` may be strided views of one cine volume (``src_ss`` / ``tar_ss`` = elements between
+    consecutive slices, 0 = contiguous): the kernel reads the frames in place, nothing is repeated or copied.
+    """
 
     @staticmethod
     def forward(ctx, v0, src, tar, moments, table, metric, num_steps, T, background, n_sectors, n_frames, B, T1,
-                src_per_pair, with_strain):
+                src_per_pair, with_strain, src_ss, tar_ss):
         v0 = v0.contiguous()
-        src = src.contiguous()
-        tar = tar.contiguous()
-        require_cuda(v0, src, tar)
+        require_cuda(v0)
+        require_cuda(src if src_ss == 0 else None, tar if tar_ss == 0 else None)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         out = _launch_shoot(v0, src, tar, moments if with_strain else None, table if with_strain else None, metric,
                             num_steps, T, background, n_sectors, n_frames, B, T1,
-                            {"m0": True, "vel": True, "sdef": True, "S": with_strain}, False, src_per_pair, need)
+                            {"m0": True, "vel": True, "sdef": True, "S": with_strain}, False, src_per_pair, need,
+                            src_slice_stride=src_ss, tar_slice_stride=tar_ss)
         ctx.cfg = (metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain)
         if need:
             ctx.save_for_backward(out["m0"], out["u"], out["traj"], src, tar, moments, table,
@@ -159,23 +172,25 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         m0, u, traj, src, tar, moments, table, counts = ctx.saved_tensors
         metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain = ctx.cfg
         P, _, H, W = m0.shape
+        src_c = src.contiguous()                       # op-level adjoint kernels take dense batches
         gu_tot = gu.contiguous().clone() if gu is not None else torch.zeros_like(u)
         dsrc = None
         if gsdef is not None:
             du = torch.empty_like(u)
             want_dsrc = ctx.needs_input_grad[1]
-            dsrc = torch.empty_like(src) if want_dsrc else None
+            dsrc = torch.empty_like(src_c) if want_dsrc else None
             if src_per_pair:
-                check(lib().b2_interp_bwd(ptr(gsdef.contiguous()), ptr(src), ptr(u), ptr(dsrc), ptr(du), P, P, P, 1,
+                check(lib().b2_interp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(dsrc), ptr(du), P, P, P, 1,
                                           H, W, 1.0, background, stream()), "b2_interp_bwd")
             else:
-                check(lib().b2_warp_bwd(ptr(gsdef.contiguous()), ptr(src), ptr(u), ptr(dsrc), ptr(du), B, T1, 1, H, W,
-                                        1.0, background, stream()), "b2_warp_bwd")
+                check(lib().b2_warp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(dsrc), ptr(du), B, T1, 1,
+                                        H, W, 1.0, background, stream()), "b2_warp_bwd")
             _lib.count_launch()
             gu_tot += du
         if with_strain and gS is not None:
             du = torch.empty_like(u)
-            check(lib().b2_strain_sector_bwd(ptr(gS.contiguous()), ptr(u), ptr(tar), ptr(moments), ptr(table),
+            tar_c = tar.reshape(B, T1, H, W).contiguous()
+            check(lib().b2_strain_sector_bwd(ptr(gS.contiguous()), ptr(u), ptr(tar_c), ptr(moments), ptr(table),
                                              ptr(counts), ptr(du), B, T1, H, W, n_sectors, n_frames, stream()),
                   "b2_strain_sector_bwd")
             _lib.count_launch()
@@ -185,7 +200,15 @@ class ShootWarpStrainFunction(torch.autograd.Function):
             gv0 = _shoot_bwd(gu_tot, gvel.contiguous() if gvel is not None else None,
                              gm0.contiguous() if gm0 is not None else None, m0, traj, metric, num_steps, T,
                              background, False)
-        return (gv0, dsrc) + (None,) * 13
+        return (gv0, dsrc) + (None,) * 15
+
+
+def _fused_size(H, W):
+    return H == W and H in (16, 32, 64, 128)
+
+
+def _rows_dense(t):
+    return t.dtype == torch.float32 and t.is_cuda and t.stride(-1) == 1 and t.stride(-2) == t.shape[-1]
 
 
 def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T=1.0, n_sectors=N_SECTORS,
@@ -194,19 +217,27 @@ def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T
 
     v0: (B*T1, 2, H, W) initial velocities, slice-major; src_vol, tar_vol: (B,1,T1,H,W)
     (the outputs of ``split_vol_to_registration_pairs(..., 'Lagrangian', output_dim=3)``;
-    only frame 0 of ``src_vol`` is read - the repeat is never materialised).
+    only frame 0 of ``src_vol`` is read - the repeat is never materialised - and ``tar_vol`` may be the
+    strided view ``vol[:, :, 1:]``: the kernel reads the cine volume in place).
     Returns the dict ``forward_volume`` hands to the trainer plus 'displacement'.
     """
     B, Cc, T1, H, W = tar_vol.shape
     if Cc != 1 or v0.shape != (B * T1, 2, H, W):
         raise _lib.B2Error(f"shape mismatch: v0 {tuple(v0.shape)}, tar_vol {tuple(tar_vol.shape)}")
-    src = src_vol[:, :, 0].contiguous()                        # (B,1,H,W) frame-0 mask
-    tar = tar_vol.reshape(B * T1, 1, H, W)
-    moments = mask_moments(src[:, 0]) if with_strain else None
+    src = src_vol[:, :, 0]                                     # (B,1,H,W) frame-0 mask (view)
+    src_ss = tar_ss = 0
+    if _fused_size(H, W) and _rows_dense(src) and _rows_dense(tar_vol) and tar_vol.stride(2) == H * W:
+        src_ss = src.stride(0) if B > 1 else H * W
+        tar_ss = tar_vol.stride(0) if B > 1 else T1 * H * W
+        tar = tar_vol
+    else:
+        src = src.contiguous()
+        tar = tar_vol.reshape(B * T1, 1, H, W).contiguous()
+    moments = mask_moments(src[:, 0].contiguous()) if with_strain else None
     table = sector_table(n_sectors, v0.device) if with_strain else None
     m0, vel, u, sdef, S = ShootWarpStrainFunction.apply(
         v0, src, tar, moments, table, metric, int(num_steps), float(T), BG[background], int(n_sectors),
-        int(n_frames), B, T1, False, bool(with_strain))
+        int(n_frames), B, T1, False, bool(with_strain), int(src_ss), int(tar_ss))
     return {
         "strain_matrix": S,
         "deformed_source": sdef.reshape(B, 1, T1, H, W),
@@ -220,5 +251,73 @@ def shoot_warp_pairs(v0, src, tar, metric: FluidMetric, num_steps=10, T=1.0, bac
     """Pairwise contract (/root/reference/modules/trainer/reg_trainer.py:45,222-225): src, tar (P,1,H,W)."""
     P, _, H, W = v0.shape
     m0, vel, u, sdef, _ = ShootWarpStrainFunction.apply(
-        v0, src, tar, None, None, metric, int(num_steps), float(T), BG[background], 3, 1, P, 1, True, False)
+        v0, src.contiguous(), tar.contiguous(), None, None, metric, int(num_steps), float(T), BG[background], 3, 1,
+        P, 1, True, False, 0, 0)
     return {"displacement": u, "velocity": vel, "momentum": m0, "deformed_source": sdef}
+
+
+class HostPipeline:
+    """Host-buffer entry point of the hot path: pinned host inputs in, strain matrices on the host out.
+
+    The batch is cut into chunks of whole slices; the H2D copy of chunk i+1 (copy stream) overlaps the
+    fused shooting kernel of chunk i (compute stream), with double-buffered device staging, so a step
+    costs max(PCIe time, kernel time) instead of their sum.  Device outputs of the whole batch stay
+    available in ``self.out`` (same keys as :func:`shoot_warp_strain`).  Inference only (no autograd).
+    """
+
+    def __init__(self, B, T, H, W, metric: FluidMetric, num_steps=10, T_end=1.0, n_sectors=N_SECTORS, n_frames=40,
+                 chunk_slices=16, device=None, background="clamp"):
+        self.dev = torch.device(device if device is not None else torch.cuda.current_device())
+        self.B, self.T, self.T1, self.H, self.W = B, T, T - 1, H, W
+        self.metric, self.num_steps, self.T_end = metric, int(num_steps), float(T_end)
+        self.n_sectors, self.n_frames, self.bg = int(n_sectors), int(n_frames), BG[background]
+        self.chunk = max(1, min(int(chunk_slices), B))
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        dev, T1, cs = self.dev, self.T1, self.chunk
+        self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
+                       "v0": torch.empty((cs * T1, 2, H, W), device=dev),
+                       "ready": torch.cuda.Event(), "free": torch.cuda.Event()} for _ in range(2)]
+        P = B * T1
+        self.out = _alloc_outputs(P, B, T1, H, W, dev, {"m0": True, "vel": True, "sdef": True, "S": True}, False,
+                                  self.n_sectors, self.n_frames, self.num_steps, False)
+        self.S_host = torch.empty((B, 1, self.n_sectors, self.n_frames), dtype=torch.float32).pin_memory()
+        self.table = sector_table(self.n_sectors, dev)
+        nbytes = lib().b2_shoot_workspace_bytes(cs, T1, H, W, self.num_steps)
+        self.ws = _workspace(nbytes, dev)
+
+    def __call__(self, v0_host: torch.Tensor, vol_host: torch.Tensor):
+        """v0_host (B*(T-1),2,H,W), vol_host (B,1,T,H,W): pinned fp32 host tensors.  Returns S on the host."""
+        B, T, T1, H, W, cs = self.B, self.T, self.T1, self.H, self.W, self.chunk
+        if tuple(vol_host.shape) != (B, 1, T, H, W) or tuple(v0_host.shape) != (B * T1, 2, H, W):
+            raise _lib.B2Error(f"shape mismatch: v0 {tuple(v0_host.shape)}, vol {tuple(vol_host.shape)}")
+        main = torch.cuda.current_stream(self.dev)
+        with torch.no_grad():
+            for i, b0 in enumerate(range(0, B, cs)):
+                b1 = min(b0 + cs, B)
+                nb = b1 - b0
+                st = self.stage[i % 2]
+                with torch.cuda.stream(self.copy_stream):
+                    if i >= 2:
+                        self.copy_stream.wait_event(st["free"])          # kernel of chunk i-2 done with this stage
+                    st["vol"][:nb].copy_(vol_host[b0:b1], non_blocking=True)
+                    st["v0"][: nb * T1].copy_(v0_host[b0 * T1: b1 * T1], non_blocking=True)
+                    st["ready"].record(self.copy_stream)
+                main.wait_event(st["ready"])
+                vol = st["vol"][:nb]                                     # (nb,1,T,H,W): read in place by the kernel
+                mom = mask_moments(vol[:, 0, 0].contiguous())
+                sl = slice(b0 * T1, b1 * T1)
+                out = {"u": self.out["u"][sl], "m0": self.out["m0"][sl], "vel": self.out["vel"][sl],
+                       "sdef": self.out["sdef"][sl], "S": self.out["S"][b0:b1], "counts": self.out["counts"][b0:b1]}
+                _launch_shoot(st["v0"][: nb * T1], vol, vol.view(-1)[H * W:], mom, self.table, self.metric,
+                              self.num_steps, self.T_end, self.bg, self.n_sectors, self.n_frames, nb, T1,
+                              {}, False, False, False, out=out, ws=self.ws,
+                              src_slice_stride=T * H * W, tar_slice_stride=T * H * W)
+                st["free"].record(main)
+                self.S_host[b0:b1].copy_(self.out["S"][b0:b1], non_blocking=True)
+        return self.S_host
+
+    def result(self):
+        """Device outputs of the last call, keyed like :func:`shoot_warp_strain`."""
+        B, T1, H, W = self.B, self.T1, self.H, self.W
+        return {"strain_matrix": self.out["S"], "deformed_source": self.out["sdef"].view(B, 1, T1, H, W),
+                "velocity": self.out["vel"], "momentum": self.out["m0"], "displacement": self.out["u"]}

@@ -271,6 +271,32 @@ def test_models_forward_volume_on_gpu(pkg, dev):
     assert set(pair) >= {"displacement", "velocity", "momentum", "deformed_source"}
 
 
+def test_host_pipeline_matches_resident(pkg, dev):
+    """Host-buffer entry point (chunked H2D/compute overlap, strided cine volume) == resident call, bit for bit."""
+    B, T, H, W, S = 5, 4, 64, 64, 4
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).pin_memory()
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 29, 2.5).pin_memory()
+    metric = pkg.FluidMetric(PARAMS)
+    pipe = pkg.HostPipeline(B, T, H, W, metric, num_steps=S, chunk_slices=2, device=dev)
+    S_host = pipe(v0, vol)
+    torch.cuda.synchronize()
+    vd = vol.to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vd, "Lagrangian", 3)
+    ref = pkg.shoot_warp_strain(v0.to(dev), sv, tv, metric, num_steps=S)           # strided views, in place
+    ref_c = pkg.shoot_warp_strain(v0.to(dev), sv.contiguous(), tv.contiguous(), metric, num_steps=S)
+    got = pipe.result()
+    for k in ("momentum", "velocity", "displacement", "deformed_source"):
+        assert torch.equal(got[k], ref[k]), k
+        assert torch.equal(ref[k], ref_c[k]), k
+    # sector sums are accumulated with shared-memory float atomics: order (hence the last bits) may differ
+    assert relerr(got["strain_matrix"], ref["strain_matrix"]) < 1e-6
+    assert relerr(ref_c["strain_matrix"], ref["strain_matrix"]) < 1e-6
+    assert relerr(S_host, ref["strain_matrix"]) < 1e-6
+    S2 = pipe(v0, vol)                                                       # reusable
+    torch.cuda.synchronize()
+    assert relerr(S2, ref["strain_matrix"]) < 1e-6
+
+
 def test_full_size_properties(pkg, dev):
     """BASELINE config-2 size (P=1536, 128^2, S=10): size-independent properties instead of the oracle."""
     B, T, H, W, S = 64, 25, 128, 128, 10
