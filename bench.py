@@ -300,7 +300,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "shoot_fwd_kernel<128,128,512> (fused flat + 10 EPDiff steps + warp + strain)",
+                "roofline": {"bound": "hbm", "kernel": "shoot_fwd_kernel<128,128,1024,clamp> (fused flat + 10 EPDiff steps + warp + strain)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": P * BYTES_PER_PAIR,
