@@ -198,7 +198,7 @@ int fluid_apply_impl(const float* f, float* out, int64_t P, int64_t H, int64_t W
       case 16: return launch_smem<16, 16, 128>(f, out, P, fp, inverse, st);
       case 32: return launch_smem<32, 32, 256>(f, out, P, fp, inverse, st);
       case 64: return launch_smem<64, 64, 256>(f, out, P, fp, inverse, st);
-      case 128: return launch_smem<128, 128, 512>(f, out, P, fp, inverse, st);
+      case 128: return launch_smem<128, 128, 1024>(f, out, P, fp, inverse, st);
     }
   }
   if (pass3_path(H, W)) {

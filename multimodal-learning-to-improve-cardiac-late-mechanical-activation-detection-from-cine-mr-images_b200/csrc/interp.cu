@@ -11,114 +11,147 @@ namespace b2 {
 
 constexpr int kThreads = 256;
 
+// pixel -> (row, col); W is a power of two for every FFT-sized grid, so the common case is a shift
+__device__ __forceinline__ void row_col(int x, int W, int wshift, int& r, int& c) {
+  if (wshift >= 0) { r = x >> wshift; c = x & (W - 1); }
+  else { r = x / W; c = x - r * W; }
+}
+
+// CT = compile-time channel count (1 or 2: the path's images/masks and vector fields); 0 = runtime C.
 // out = interp(I, u, dt) [+ dt*u when ADD_U: compose_disp_vel]
-template <int BG, bool ADD_U>
+template <int BG, bool ADD_U, int CT>
 __global__ void __launch_bounds__(kThreads)
 interp_fwd_kernel(const float* __restrict__ I, const float* __restrict__ u, float* __restrict__ out,
-                  int P, int sI, int gI, int su, int C, int H, int W, float dt) {
+                  int P, int sI, int gI, int su, int C, int H, int W, int wshift, float dt) {
   const int N = H * W;
   const int x = blockIdx.x * kThreads + threadIdx.x;
   if (x >= N) return;
-  const int r = x / W, c = x - r * W;
+  int r, c;
+  row_col(x, W, wshift, r, c);
+  const int nc = CT ? CT : C;
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
-    const float* up = u + (size_t)p * su * 2 * N;
-    const float u0 = up[x], u1 = up[N + x];
+    const float* up = u + (size_t)(p * su) * 2 * N + x;
+    const float u0 = up[0], u1 = up[N];
     const Taps t = make_taps<BG>((float)r + dt * u0, (float)c + dt * u1, H, W);
-    const float* Ip = I + (size_t)(p / gI) * sI * C * N;
-    float* op = out + (size_t)p * C * N;
-    for (int ch = 0; ch < C; ++ch) {
-      const float* Ic = Ip + (size_t)ch * N;
-      float v = tap_sample<BG>(t, Ic[t.o00], Ic[t.o10], Ic[t.o01], Ic[t.o11]);
-      if (ADD_U) v += dt * (ch == 0 ? u0 : u1);
-      op[(size_t)ch * N + x] = v;
+    const float* Ic = I + (size_t)((p / gI) * sI) * nc * N;
+    float* op = out + (size_t)p * nc * N + x;
+#pragma unroll
+    for (int ch = 0; ch < (CT ? CT : 1); ++ch) {
+      for (int cc = 0; cc < (CT ? 1 : C); ++cc) {
+        float v = tap_sample<BG>(t, Ic[t.o00], Ic[t.o10], Ic[t.o01], Ic[t.o11]);
+        if (ADD_U) v += dt * ((CT ? ch : cc) == 0 ? u0 : u1);
+        *op = v;
+        Ic += N;
+        op += N;
+      }
     }
   }
 }
 
 // dI += splat(gout) ; du = dt * sum_c gout_c * grad I_c(x + dt u) [+ dt*gout when ADD_U]
-template <int BG, bool ADD_U, bool NEED_DI, bool NEED_DU>
+template <int BG, bool ADD_U, bool NEED_DI, bool NEED_DU, int CT>
 __global__ void __launch_bounds__(kThreads)
 interp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ I, const float* __restrict__ u,
                   float* __restrict__ dI, float* __restrict__ du,
-                  int P, int sI, int gI, int su, int C, int H, int W, float dt) {
+                  int P, int sI, int gI, int su, int C, int H, int W, int wshift, float dt) {
   const int N = H * W;
   const int x = blockIdx.x * kThreads + threadIdx.x;
   if (x >= N) return;
-  const int r = x / W, c = x - r * W;
+  int r, c;
+  row_col(x, W, wshift, r, c);
+  const int nc = CT ? CT : C;
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
-    const float* up = u + (size_t)p * su * 2 * N;
-    const float u0 = up[x], u1 = up[N + x];
+    const float* up = u + (size_t)(p * su) * 2 * N + x;
+    const float u0 = up[0], u1 = up[N];
     const Taps t = make_taps<BG>((float)r + dt * u0, (float)c + dt * u1, H, W);
     const float oma = 1.f - t.a, omb = 1.f - t.b;
     float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
     if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
-    const float* Ip = I + (size_t)(p / gI) * sI * C * N;
-    float* dIp = NEED_DI ? dI + (size_t)(p / gI) * sI * C * N : nullptr;
-    const float* gp = gout + (size_t)p * C * N;
+    const size_t ioff = (size_t)((p / gI) * sI) * nc * N;
+    const float* Ic = I + ioff;
+    float* dIc = NEED_DI ? dI + ioff : nullptr;
+    const float* gp = gout + (size_t)p * nc * N + x;
     float a0 = 0.f, a1 = 0.f;
-    for (int ch = 0; ch < C; ++ch) {
-      const float g = gp[(size_t)ch * N + x];
-      if (NEED_DI) {
-        float* d = dIp + (size_t)ch * N;
-        atomicAdd(d + t.o00, w00 * g);
-        atomicAdd(d + t.o01, w01 * g);
-        atomicAdd(d + t.o10, w10 * g);
-        atomicAdd(d + t.o11, w11 * g);
-      }
-      if (NEED_DU) {
-        const float* Ic = Ip + (size_t)ch * N;
-        float g0, g1;
-        tap_grad<BG>(t, Ic[t.o00], Ic[t.o10], Ic[t.o01], Ic[t.o11], g0, g1);
-        a0 += g * g0;
-        a1 += g * g1;
-        if (ADD_U) { if (ch == 0) a0 += g; else a1 += g; }
+#pragma unroll
+    for (int ch = 0; ch < (CT ? CT : 1); ++ch) {
+      for (int cc = 0; cc < (CT ? 1 : C); ++cc) {
+        const float g = *gp;
+        if (NEED_DI) {
+          atomicAdd(dIc + t.o00, w00 * g);
+          atomicAdd(dIc + t.o01, w01 * g);
+          atomicAdd(dIc + t.o10, w10 * g);
+          atomicAdd(dIc + t.o11, w11 * g);
+          dIc += N;
+        }
+        if (NEED_DU) {
+          float g0, g1;
+          tap_grad<BG>(t, Ic[t.o00], Ic[t.o10], Ic[t.o01], Ic[t.o11], g0, g1);
+          a0 += g * g0;
+          a1 += g * g1;
+          if (ADD_U) { if ((CT ? ch : cc) == 0) a0 += g; else a1 += g; }
+        }
+        Ic += N;
+        gp += N;
       }
     }
     if (NEED_DU) {
-      float* dup = du + (size_t)p * su * 2 * N;
+      float* dup = du + (size_t)(p * su) * 2 * N + x;
       if (su == 0) {  // broadcast u: reduce over the batch
-        atomicAdd(dup + x, dt * a0);
-        atomicAdd(dup + N + x, dt * a1);
+        atomicAdd(dup, dt * a0);
+        atomicAdd(dup + N, dt * a1);
       } else {
-        dup[x] = dt * a0;
-        dup[N + x] = dt * a1;
+        dup[0] = dt * a0;
+        dup[N] = dt * a1;
       }
     }
   }
 }
 
-template <int BG>
+template <int BG, int CT>
 __global__ void __launch_bounds__(kThreads)
 splat_fwd_kernel(const float* __restrict__ J, const float* __restrict__ u, float* __restrict__ out,
-                 float* __restrict__ wout, int P, int sJ, int su, int C, int H, int W, float dt) {
+                 float* __restrict__ wout, int P, int sJ, int su, int C, int H, int W, int wshift, float dt) {
   const int N = H * W;
   const int x = blockIdx.x * kThreads + threadIdx.x;
   if (x >= N) return;
-  const int r = x / W, c = x - r * W;
+  int r, c;
+  row_col(x, W, wshift, r, c);
+  const int nc = CT ? CT : C;
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
-    const float* up = u + (size_t)p * su * 2 * N;
-    const Taps t = make_taps<BG>((float)r + dt * up[x], (float)c + dt * up[N + x], H, W);
+    const float* up = u + (size_t)(p * su) * 2 * N + x;
+    const Taps t = make_taps<BG>((float)r + dt * up[0], (float)c + dt * up[N], H, W);
     const float oma = 1.f - t.a, omb = 1.f - t.b;
     float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
     if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
-    const float* Jp = J + (size_t)p * sJ * C * N;
-    float* op = out + (size_t)p * C * N;
-    for (int ch = 0; ch < C; ++ch) {
-      const float g = Jp[(size_t)ch * N + x];
-      float* d = op + (size_t)ch * N;
-      atomicAdd(d + t.o00, w00 * g);
-      atomicAdd(d + t.o01, w01 * g);
-      atomicAdd(d + t.o10, w10 * g);
-      atomicAdd(d + t.o11, w11 * g);
+    const float* Jc = J + (size_t)(p * sJ) * nc * N + x;
+    float* d = out + (size_t)p * nc * N;
+#pragma unroll
+    for (int ch = 0; ch < (CT ? CT : 1); ++ch) {
+      for (int cc = 0; cc < (CT ? 1 : C); ++cc) {
+        const float g = *Jc;
+        atomicAdd(d + t.o00, w00 * g);
+        atomicAdd(d + t.o01, w01 * g);
+        atomicAdd(d + t.o10, w10 * g);
+        atomicAdd(d + t.o11, w11 * g);
+        Jc += N;
+        d += N;
+      }
     }
     if (wout) {
-      float* d = wout + (size_t)p * N;
-      atomicAdd(d + t.o00, w00);
-      atomicAdd(d + t.o01, w01);
-      atomicAdd(d + t.o10, w10);
-      atomicAdd(d + t.o11, w11);
+      float* dw = wout + (size_t)p * N;
+      atomicAdd(dw + t.o00, w00);
+      atomicAdd(dw + t.o01, w01);
+      atomicAdd(dw + t.o10, w10);
+      atomicAdd(dw + t.o11, w11);
     }
   }
+}
+
+static int log2_or_neg(int64_t W) {
+  if (W <= 0 || (W & (W - 1))) return -1;
+  int s = 0;
+  while ((int64_t(1) << s) < W) ++s;
+  return s;
 }
 
 static int check_dims(int64_t P, int64_t PI, int64_t Pu, int64_t C, int64_t H, int64_t W) {
@@ -136,13 +169,34 @@ template <bool ADD_U>
 static int launch_interp_fwd(const float* I, const float* u, float* out, int64_t P, int64_t PI, int64_t Pu,
                              int64_t C, int64_t H, int64_t W, float dt, int bg, cudaStream_t st, int gI = 1) {
   dim3 grid = pixel_grid(P, H * W);
-  const int sI = (PI == P || gI > 1) ? 1 : 0, su = Pu == P ? 1 : 0;
-  if (bg == B2_BG_CLAMP)
-    interp_fwd_kernel<B2_BG_CLAMP, ADD_U><<<grid, kThreads, 0, st>>>(I, u, out, (int)P, sI, gI, su, (int)C, (int)H, (int)W, dt);
-  else
-    interp_fwd_kernel<B2_BG_ZERO, ADD_U><<<grid, kThreads, 0, st>>>(I, u, out, (int)P, sI, gI, su, (int)C, (int)H, (int)W, dt);
+  const int sI = (PI == P || gI > 1) ? 1 : 0, su = Pu == P ? 1 : 0, ws = log2_or_neg(W);
+#define B2_LAUNCH_FWD(BGV, CTV)                                                                       \
+  interp_fwd_kernel<BGV, ADD_U, CTV><<<grid, kThreads, 0, st>>>(I, u, out, (int)P, sI, gI, su, (int)C, \
+                                                               (int)H, (int)W, ws, dt)
+  if (bg == B2_BG_CLAMP) {
+    if (C == 1) B2_LAUNCH_FWD(B2_BG_CLAMP, 1);
+    else if (C == 2) B2_LAUNCH_FWD(B2_BG_CLAMP, 2);
+    else B2_LAUNCH_FWD(B2_BG_CLAMP, 0);
+  } else {
+    if (C == 1) B2_LAUNCH_FWD(B2_BG_ZERO, 1);
+    else if (C == 2) B2_LAUNCH_FWD(B2_BG_ZERO, 2);
+    else B2_LAUNCH_FWD(B2_BG_ZERO, 0);
+  }
+#undef B2_LAUNCH_FWD
   B2_CHECK_LAUNCH();
   return B2_OK;
+}
+
+template <bool ADD_U, int BGV, int CTV>
+static void launch_bwd_variant(dim3 grid, const float* gout, const float* I, const float* u, float* dI, float* du,
+                               int P, int sI, int gI, int su, int C, int H, int W, int ws, float dt,
+                               cudaStream_t st) {
+  if (dI && du)
+    interp_bwd_kernel<BGV, ADD_U, true, true, CTV><<<grid, kThreads, 0, st>>>(gout, I, u, dI, du, P, sI, gI, su, C, H, W, ws, dt);
+  else if (dI)
+    interp_bwd_kernel<BGV, ADD_U, true, false, CTV><<<grid, kThreads, 0, st>>>(gout, I, u, dI, du, P, sI, gI, su, C, H, W, ws, dt);
+  else
+    interp_bwd_kernel<BGV, ADD_U, false, true, CTV><<<grid, kThreads, 0, st>>>(gout, I, u, dI, du, P, sI, gI, su, C, H, W, ws, dt);
 }
 
 template <bool ADD_U>
@@ -152,22 +206,21 @@ static int launch_interp_bwd(const float* gout, const float* I, const float* u, 
   if (!dI && !du) return B2_OK;
   const int64_t N = H * W;
   dim3 grid = pixel_grid(P, N);
-  const int sI = (PI == P || gI > 1) ? 1 : 0, su = Pu == P ? 1 : 0;
+  const int sI = (PI == P || gI > 1) ? 1 : 0, su = Pu == P ? 1 : 0, ws = log2_or_neg(W);
   if (dI) B2_CUDA(cudaMemsetAsync(dI, 0, sizeof(float) * (size_t)PI * C * N, st));
   if (du && su == 0) B2_CUDA(cudaMemsetAsync(du, 0, sizeof(float) * 2 * N, st));
-#define B2_LAUNCH_BWD(BGV, DI, DU)                                                              \
-  interp_bwd_kernel<BGV, ADD_U, DI, DU><<<grid, kThreads, 0, st>>>(gout, I, u, dI, du, (int)P, sI, gI, su, \
-                                                                  (int)C, (int)H, (int)W, dt)
+#define B2_BWD(BGV, CTV) \
+  launch_bwd_variant<ADD_U, BGV, CTV>(grid, gout, I, u, dI, du, (int)P, sI, gI, su, (int)C, (int)H, (int)W, ws, dt, st)
   if (bg == B2_BG_CLAMP) {
-    if (dI && du) B2_LAUNCH_BWD(B2_BG_CLAMP, true, true);
-    else if (dI) B2_LAUNCH_BWD(B2_BG_CLAMP, true, false);
-    else B2_LAUNCH_BWD(B2_BG_CLAMP, false, true);
+    if (C == 1) B2_BWD(B2_BG_CLAMP, 1);
+    else if (C == 2) B2_BWD(B2_BG_CLAMP, 2);
+    else B2_BWD(B2_BG_CLAMP, 0);
   } else {
-    if (dI && du) B2_LAUNCH_BWD(B2_BG_ZERO, true, true);
-    else if (dI) B2_LAUNCH_BWD(B2_BG_ZERO, true, false);
-    else B2_LAUNCH_BWD(B2_BG_ZERO, false, true);
+    if (C == 1) B2_BWD(B2_BG_ZERO, 1);
+    else if (C == 2) B2_BWD(B2_BG_ZERO, 2);
+    else B2_BWD(B2_BG_ZERO, 0);
   }
-#undef B2_LAUNCH_BWD
+#undef B2_BWD
   B2_CHECK_LAUNCH();
   return B2_OK;
 }
@@ -204,10 +257,19 @@ extern "C" int b2_splat_fwd(const float* J, const float* u, float* out, float* w
   if (wout) B2_CUDA(cudaMemsetAsync(wout, 0, sizeof(float) * (size_t)P * N, st));
   dim3 grid = pixel_grid(P, N);
   const int sJ = PJ == P ? 1 : 0, su = Pu == P ? 1 : 0;
-  if (background == B2_BG_CLAMP)
-    splat_fwd_kernel<B2_BG_CLAMP><<<grid, kThreads, 0, st>>>(J, u, out, wout, (int)P, sJ, su, (int)C, (int)H, (int)W, dt);
-  else
-    splat_fwd_kernel<B2_BG_ZERO><<<grid, kThreads, 0, st>>>(J, u, out, wout, (int)P, sJ, su, (int)C, (int)H, (int)W, dt);
+  const int ws = log2_or_neg(W);
+#define B2_SPLAT(BGV, CTV) \
+  splat_fwd_kernel<BGV, CTV><<<grid, kThreads, 0, st>>>(J, u, out, wout, (int)P, sJ, su, (int)C, (int)H, (int)W, ws, dt)
+  if (background == B2_BG_CLAMP) {
+    if (C == 1) B2_SPLAT(B2_BG_CLAMP, 1);
+    else if (C == 2) B2_SPLAT(B2_BG_CLAMP, 2);
+    else B2_SPLAT(B2_BG_CLAMP, 0);
+  } else {
+    if (C == 1) B2_SPLAT(B2_BG_ZERO, 1);
+    else if (C == 2) B2_SPLAT(B2_BG_ZERO, 2);
+    else B2_SPLAT(B2_BG_ZERO, 0);
+  }
+#undef B2_SPLAT
   B2_CHECK_LAUNCH();
   return B2_OK;
 }

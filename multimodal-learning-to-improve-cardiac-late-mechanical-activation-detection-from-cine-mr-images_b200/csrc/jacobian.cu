@@ -103,49 +103,77 @@ jtv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const f
   }
 }
 
+// pixel -> (row, col); shift when W is a power of two
+__device__ __forceinline__ void row_col_j(int x, int W, int wshift, int& r, int& c) {
+  if (wshift >= 0) { r = x >> wshift; c = x & (W - 1); }
+  else { r = x / W; c = x - r * W; }
+}
+
 // m = (I + Du)^T (m0 o (id + u))
 template <int BG>
 __global__ void __launch_bounds__(kThreadsJ)
 adstar_fwd_kernel(const float* __restrict__ u, const float* __restrict__ m0, float* __restrict__ out,
-                  int P, int H, int W) {
+                  int P, int H, int W, int wshift) {
   const int N = H * W;
   const int x = blockIdx.x * kThreadsJ + threadIdx.x;
   if (x >= N) return;
-  const int r = x / W, c = x - r * W;
+  int r, c;
+  row_col_j(x, W, wshift, r, c);
+  int rlo, rhi, clo, chi; float sr, sc;
+  diff_idx(r, H, rlo, rhi, sr);
+  diff_idx(c, W, clo, chi, sc);
+  const int oup = rlo * W + c, odn = rhi * W + c, olf = r * W + clo, ort = r * W + chi;
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
-    const float* up = u + (size_t)p * 2 * N;
+    const float* u0 = u + (size_t)p * 2 * N;
+    const float* u1 = u0 + N;
     const float* mp = m0 + (size_t)p * 2 * N;
-    const Jac J = jac_at(up, up + N, r, c, H, W);
-    const Taps t = make_taps<BG>((float)r + up[x], (float)c + up[N + x], H, W);
+    const float d00 = sr * (u0[odn] - u0[oup]), d10 = sr * (u1[odn] - u1[oup]);
+    const float d01 = sc * (u0[ort] - u0[olf]), d11 = sc * (u1[ort] - u1[olf]);
+    const Taps t = make_taps<BG>((float)r + u0[x], (float)c + u1[x], H, W);
     const float w0 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
-    const float w1 = tap_sample<BG>(t, mp[N + t.o00], mp[N + t.o10], mp[N + t.o01], mp[N + t.o11]);
-    float* op = out + (size_t)p * 2 * N;
-    op[x] = w0 + (J.d00 * w0 + J.d10 * w1);
-    op[N + x] = w1 + (J.d01 * w0 + J.d11 * w1);
+    mp += N;
+    const float w1 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
+    float* op = out + (size_t)p * 2 * N + x;
+    op[0] = w0 + (d00 * w0 + d10 * w1);
+    op[N] = w1 + (d01 * w0 + d11 * w1);
   }
 }
 
-// Adjoint of adstar_fwd given wbuf = m0 o (id+u).
+// Adjoint of adstar_fwd given wbuf = m0 o (id+u).  du = [du_add +] interp part + Jacobian part.
+// The transposed difference is evaluated in gathered form with per-pixel coefficients
+//   (D^T q)[k] = cm q[k-1] + c0 q[k] - cp q[k+1],
+//   cm = [k>=1] s(k-1), cp = [k<=n-2] s(k+1), c0 = [k==n-1] - [k==0],  s = 1 at the ends, 1/2 inside.
 template <int BG, bool NEED_DU, bool NEED_DM>
 __global__ void __launch_bounds__(kThreadsJ)
 adstar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ m0,
-                  const float* __restrict__ wbuf, float* __restrict__ du, float* __restrict__ dm0,
-                  int P, int H, int W) {
+                  const float* __restrict__ wbuf, const float* __restrict__ du_add, float* __restrict__ du,
+                  float* __restrict__ dm0, int P, int H, int W, int wshift) {
   const int N = H * W;
   const int x = blockIdx.x * kThreadsJ + threadIdx.x;
   if (x >= N) return;
-  const int r = x / W, c = x - r * W;
+  int r, c;
+  row_col_j(x, W, wshift, r, c);
+  int rlo, rhi, clo, chi; float sr, sc;
+  diff_idx(r, H, rlo, rhi, sr);
+  diff_idx(c, W, clo, chi, sc);
+  const int oup = rlo * W + c, odn = rhi * W + c, olf = r * W + clo, ort = r * W + chi;
+  const float cmr = (r >= 1) ? diff_scale(r - 1, H) : 0.f, cpr = (r <= H - 2) ? diff_scale(r + 1, H) : 0.f;
+  const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
+  const float cmc = (c >= 1) ? diff_scale(c - 1, W) : 0.f, cpc = (c <= W - 2) ? diff_scale(c + 1, W) : 0.f;
+  const float c0c = (c == W - 1 ? 1.f : 0.f) - (c == 0 ? 1.f : 0.f);
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
-    const float* up = u + (size_t)p * 2 * N;
+    const float* u0 = u + (size_t)p * 2 * N;
+    const float* u1 = u0 + N;
     const float* mp = m0 + (size_t)p * 2 * N;
-    const float* gp = g + (size_t)p * 2 * N;
-    const float* wp = wbuf + (size_t)p * 2 * N;
-    const Jac J = jac_at(up, up + N, r, c, H, W);
-    const float g0 = gp[x], g1 = gp[N + x];
+    const float* g0p = g + (size_t)p * 2 * N;
+    const float* g1p = g0p + N;
+    const float d00 = sr * (u0[odn] - u0[oup]), d10 = sr * (u1[odn] - u1[oup]);
+    const float d01 = sc * (u0[ort] - u0[olf]), d11 = sc * (u1[ort] - u1[olf]);
+    const float g0 = g0p[x], g1 = g1p[x];
     // gw = (I + Du) g
-    const float gw0 = g0 + (J.d00 * g0 + J.d01 * g1);
-    const float gw1 = g1 + (J.d10 * g0 + J.d11 * g1);
-    const Taps t = make_taps<BG>((float)r + up[x], (float)c + up[N + x], H, W);
+    const float gw0 = g0 + (d00 * g0 + d01 * g1);
+    const float gw1 = g1 + (d10 * g0 + d11 * g1);
+    const Taps t = make_taps<BG>((float)r + u0[x], (float)c + u1[x], H, W);
     if (NEED_DM) {
       const float oma = 1.f - t.a, omb = 1.f - t.b;
       float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
@@ -160,23 +188,36 @@ adstar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, cons
     if (NEED_DU) {
       float a0, a1, b0, b1;
       tap_grad<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11], a0, a1);
-      tap_grad<BG>(t, mp[N + t.o00], mp[N + t.o10], mp[N + t.o01], mp[N + t.o11], b0, b1);
+      mp += N;
+      tap_grad<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11], b0, b1);
       float o0 = gw0 * a0 + gw1 * b0;
       float o1 = gw0 * a1 + gw1 * b1;
-      // Jacobian part: m_a = ... + sum_b (d_a u_b) w_b  ->  du_b += sum_a D_a^T (g_a w_b)
-      float g0u, g0d, g0l, g0r, g0c, g1u, g1d, g1l, g1r, g1c;
-      float w0u, w0d, w0l, w0r, w0c, w1u, w1d, w1l, w1r, w1c;
-      load5(gp, r, c, H, W, g0u, g0d, g0l, g0r, g0c);
-      load5(gp + N, r, c, H, W, g1u, g1d, g1l, g1r, g1c);
-      load5(wp, r, c, H, W, w0u, w0d, w0l, w0r, w0c);
-      load5(wp + N, r, c, H, W, w1u, w1d, w1l, w1r, w1c);
-      o0 += diffT(g0u * w0u, g0c * w0c, g0d * w0d, r, H) + diffT(g1l * w0l, g1c * w0c, g1r * w0r, c, W);
-      o1 += diffT(g0u * w1u, g0c * w1c, g0d * w1d, r, H) + diffT(g1l * w1l, g1c * w1c, g1r * w1r, c, W);
-      float* dp = du + (size_t)p * 2 * N;
-      dp[x] = o0;
-      dp[N + x] = o1;
+      // Jacobian part: m_a = ... + sum_b (d_a u_b) w_b  ->  du_b += D_0^T (g_0 w_b) + D_1^T (g_1 w_b)
+      const float* w0p = wbuf + (size_t)p * 2 * N;
+      const float* w1p = w0p + N;
+      const float gu = g0p[oup], gd = g0p[odn], gl = g1p[olf], gr = g1p[ort];
+      const float w0c = w0p[x], w1c = w1p[x];
+      o0 += (cmr * (gu * w0p[oup]) + c0r * (g0 * w0c) - cpr * (gd * w0p[odn]))
+          + (cmc * (gl * w0p[olf]) + c0c * (g1 * w0c) - cpc * (gr * w0p[ort]));
+      o1 += (cmr * (gu * w1p[oup]) + c0r * (g0 * w1c) - cpr * (gd * w1p[odn]))
+          + (cmc * (gl * w1p[olf]) + c0c * (g1 * w1c) - cpc * (gr * w1p[ort]));
+      float* dp = du + (size_t)p * 2 * N + x;
+      if (du_add) {
+        const float* ap = du_add + (size_t)p * 2 * N + x;
+        o0 += ap[0];
+        o1 += ap[N];
+      }
+      dp[0] = o0;
+      dp[N] = o1;
     }
   }
+}
+
+static int log2_or_neg_j(int64_t W) {
+  if (W <= 0 || (W & (W - 1))) return -1;
+  int s = 0;
+  while ((int64_t(1) << s) < W) ++s;
+  return s;
 }
 
 static int check_pf(int64_t P, int64_t H, int64_t W) {
@@ -223,17 +264,19 @@ extern "C" int b2_adstar_fwd(const float* u, const float* m0, float* out, int64_
   if (int e = check_pf(P, H, W)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (background == B2_BG_CLAMP)
-    adstar_fwd_kernel<B2_BG_CLAMP><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(u, m0, out, (int)P, (int)H, (int)W);
+    adstar_fwd_kernel<B2_BG_CLAMP><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(u, m0, out, (int)P, (int)H, (int)W, log2_or_neg_j(W));
   else if (background == B2_BG_ZERO)
-    adstar_fwd_kernel<B2_BG_ZERO><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(u, m0, out, (int)P, (int)H, (int)W);
+    adstar_fwd_kernel<B2_BG_ZERO><<<pgrid(P, H * W), kThreadsJ, 0, st>>>(u, m0, out, (int)P, (int)H, (int)W, log2_or_neg_j(W));
   else return B2_E_PARAM;
   B2_CHECK_LAUNCH();
   return B2_OK;
 }
 
 namespace b2 {
+// du_add (optional): a (P,2,H,W) field added into du (lets the adjoint sweep skip a separate axpy pass)
 int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* du, float* dm0, float* workspace,
-                    int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st) {
+                    int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st,
+                    const float* du_add) {
   if (!gout || !u || !m0) return B2_E_NULL;
   if (!du && !dm0) return B2_OK;
   if (int e = check_pf(P, H, W)) return e;
@@ -246,7 +289,8 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
   if (dm0 && zero_dm0) B2_CUDA(cudaMemsetAsync(dm0, 0, sizeof(float) * (size_t)P * 2 * N, st));
   dim3 grid = pgrid(P, N);
 #define B2_LAUNCH_AD(BGV, DU, DM) \
-  adstar_bwd_kernel<BGV, DU, DM><<<grid, kThreadsJ, 0, st>>>(gout, u, m0, workspace, du, dm0, (int)P, (int)H, (int)W)
+  adstar_bwd_kernel<BGV, DU, DM><<<grid, kThreadsJ, 0, st>>>(gout, u, m0, workspace, du_add, du, dm0, (int)P, (int)H, (int)W, \
+                                                             log2_or_neg_j(W))
   if (background == B2_BG_CLAMP) {
     if (du && dm0) B2_LAUNCH_AD(B2_BG_CLAMP, true, true);
     else if (du) B2_LAUNCH_AD(B2_BG_CLAMP, true, false);
@@ -264,5 +308,5 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
 
 extern "C" int b2_adstar_bwd(const float* gout, const float* u, const float* m0, float* du, float* dm0,
                              float* workspace, int64_t P, int64_t H, int64_t W, int background, void* stream) {
-  return b2::adstar_bwd_impl(gout, u, m0, du, dm0, workspace, P, H, W, background, true, (cudaStream_t)stream);
+  return b2::adstar_bwd_impl(gout, u, m0, du, dm0, workspace, P, H, W, background, true, (cudaStream_t)stream, nullptr);
 }

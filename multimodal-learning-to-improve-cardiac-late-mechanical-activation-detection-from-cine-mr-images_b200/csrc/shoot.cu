@@ -26,7 +26,8 @@ namespace b2 {
 int fluid_apply_impl(const float* f, float* out, int64_t P, int64_t H, int64_t W, float alpha, float beta,
                      float gamma, int inverse, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* du, float* dm0, float* workspace,
-                    int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st);
+                    int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st,
+                    const float* du_add);
 
 constexpr int kFusedMaxSectors = 256;
 #ifndef B2_FAST_GATHER
@@ -439,8 +440,8 @@ extern "C" int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0
       if (int e = axpby(g_m0, g_v, 1.f, 1.f, n, st)) return e;
     } else {
       // m_s = Ad*_{u_s} m0: du -> g_u (dead after compose_bwd), dm0 accumulated into g_m0
-      if (int e = adstar_bwd_impl(g_v, u_s, m0, g_u, g_m0, wbuf, P, H, W, background, /*zero_dm0=*/false, st)) return e;
-      if (int e = axpby(g_u, g_uc, 1.f, 1.f, n, st)) return e;
+      // (the compose part g_uc is added inside the kernel)
+      if (int e = adstar_bwd_impl(g_v, u_s, m0, g_u, g_m0, wbuf, P, H, W, background, /*zero_dm0=*/false, st, g_uc)) return e;
     }
   }
   if (v0_is_momentum) {   // the input was m0 itself: return dL/dm0
