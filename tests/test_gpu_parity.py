@@ -80,6 +80,51 @@ def test_splat(pkg, oracle, dev, bg):
     assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 2, 2), (1, 1, 3, 130), (70000, 1, 4, 4)])
+def test_interp_edge_shapes(pkg, oracle, dev, shape):
+    """Minimum grid, generic channel count, ragged width, and more pairs than gridDim.y (65535)."""
+    P, C, H, W = shape
+    I, u = _rand(P, C, H, W, seed=31), 1.5 * _rand(P, 2, H, W, seed=32)
+    out = pkg.interp(I.to(dev), u.to(dev), 1.0)
+    assert relerr(out, oracle.interp(I, u, 1.0)) < TOL
+    if P <= 2:
+        _check_op(dev, lambda a, b: pkg.interp(a, b), lambda a, b: oracle.interp(a, b), [I, u])
+        _check_op(dev, lambda a, b: pkg.splat(a, b), lambda a, b: oracle.splat(a, b), [I, u])
+
+
+@pytest.mark.parametrize("S", [1, 2, 3])
+def test_shoot_step_parity(pkg, oracle, dev, S):
+    """Odd and even step counts exercise both ping-pong parities of the displacement buffers; B=1, T=2."""
+    H = W = 32
+    src_vol, tar_vol = _masks(pkg, 1, 2, H, W)
+    v0 = _smooth_v0(pkg, 1, H, W, 33, 3.0)
+    ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, n_sectors=18, n_frames=2)
+    out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S,
+                                n_sectors=18, n_frames=2)
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
+        assert relerr(out[k], ref[k]) < TOL, f"{k}: {relerr(out[k], ref[k]):.2e}"
+    vz = v0.to(dev).requires_grad_(True)
+    pkg.shoot_warp_strain(vz, src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S,
+                          n_sectors=18, n_frames=2)["displacement"].sum().backward()
+    vc = v0.clone().requires_grad_(True)
+    oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, n_sectors=18, n_frames=2)["displacement"].sum().backward()
+    assert relerr(vz.grad, vc.grad) < 5e-5
+
+
+def test_zero_background_shooting(pkg, oracle, dev):
+    """D1-alt (zero background) through the fused kernel."""
+    H = W = 32
+    S = 3
+    src_vol, tar_vol = _masks(pkg, 2, 3, H, W)
+    v0 = _smooth_v0(pkg, 4, H, W, 34, 3.0)
+    conv = oracle.Conventions(background="zero")
+    ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, conv=conv)
+    out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S,
+                                background="zero")
+    for k in ("momentum", "velocity", "displacement", "deformed_source"):
+        assert relerr(out[k], ref[k]) < TOL, f"{k}: {relerr(out[k], ref[k]):.2e}"
+
+
 def test_errors_on_gpu(pkg, dev):
     with pytest.raises(RuntimeError):
         pkg.interp(torch.zeros(2, 1, 8, 8, device=dev), torch.zeros(3, 2, 8, 8, device=dev))
