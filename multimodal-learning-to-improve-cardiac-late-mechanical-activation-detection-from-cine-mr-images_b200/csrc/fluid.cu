@@ -184,6 +184,127 @@ static int launch_3pass(const float* f, float* out, int64_t P, FluidParams fp, i
   return B2_OK;
 }
 
+// ------------------------------------------------------------------ path B, fused EPDiff-step row kernels
+// For grids that do not fit one SM (256x256, rectangular) an EPDiff step is three kernels instead of five:
+//   adstar_rows_kernel : m = Ad*_u m0 computed per row band (u band + halo staged in shared memory, stencil
+//                        from shared memory, m0 gathered from global) and row-FFT'd in place -> spectrum scratch
+//   fft_cols_kernel    : column FFT + symbol multiply + column IFFT (above)
+//   compose_rows_kernel: row IFFT -> v, then u_next = interp(u, v, -dt) - dt v gathered from global
+// so m and v never round-trip through HBM (64*N instead of 96*N bytes per step).
+constexpr int kBandRows = 16;
+
+template <int W, int BG>
+__global__ void __launch_bounds__(kNTB)
+adstar_rows_kernel(const float* __restrict__ u, const float* __restrict__ m0, float2* __restrict__ zg, int H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LD = W + 1, RB = kBandRows;
+  float2* z = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = z + RB * LD;
+  float2* ub = tw + W;                       // (RB+2) x W interleaved u rows, edge rows replicated
+  const int tid = threadIdx.x, p = blockIdx.y, row0 = blockIdx.x * RB;
+  const int N = H * W;
+  init_twiddles<W>(tw, tid, kNTB);
+  const float* u0 = u + (size_t)p * 2 * N;
+  const float* u1 = u0 + N;
+  for (int i = tid; i < (RB + 2) * W; i += kNTB) {
+    const int k = i / W, c = i % W;
+    const int r = min(max(row0 - 1 + k, 0), H - 1);
+    ub[i] = make_float2(u0[r * W + c], u1[r * W + c]);
+  }
+  __syncthreads();
+  const float* mp = m0 + (size_t)p * 2 * N;
+  for (int i = tid; i < RB * W; i += kNTB) {
+    const int rr = i / W, c = i % W, r = row0 + rr;
+    const float2 ce = ub[(rr + 1) * W + c], up = ub[rr * W + c], dn = ub[(rr + 2) * W + c];
+    const float2 lf = ub[(rr + 1) * W + max(c - 1, 0)], rt = ub[(rr + 1) * W + min(c + 1, W - 1)];
+    const float sr = (r == 0 || r == H - 1) ? 1.f : 0.5f, sc = (c == 0 || c == W - 1) ? 1.f : 0.5f;
+    const float d00 = sr * (dn.x - up.x), d10 = sr * (dn.y - up.y);
+    const float d01 = sc * (rt.x - lf.x), d11 = sc * (rt.y - lf.y);
+    const Taps t = make_taps<BG>((float)r + ce.x, (float)c + ce.y, H, W);
+    const float w0 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
+    const float w1 = tap_sample<BG>(t, mp[N + t.o00], mp[N + t.o10], mp[N + t.o01], mp[N + t.o11]);
+    z[rr * LD + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+  }
+  __syncthreads();
+  fft_lines<W, RB, -1, kNTB, 1, LD>(z, tw, tid);
+  float2* zp = zg + (size_t)p * N + (size_t)row0 * W;
+  for (int i = tid; i < RB * W; i += kNTB) zp[i] = z[(i / W) * LD + (i % W)];
+}
+
+template <int W, int BG>
+__global__ void __launch_bounds__(kNTB)
+compose_rows_kernel(const float2* __restrict__ zg, const float* __restrict__ u, float* __restrict__ unext,
+                    float* __restrict__ vout, int H, float mdt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LD = W + 1, RB = kBandRows;
+  float2* z = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = z + RB * LD;
+  const int tid = threadIdx.x, p = blockIdx.y, row0 = blockIdx.x * RB;
+  const int N = H * W;
+  init_twiddles<W>(tw, tid, kNTB);
+  const float2* zp = zg + (size_t)p * N + (size_t)row0 * W;
+  for (int i = tid; i < RB * W; i += kNTB) z[(i / W) * LD + (i % W)] = zp[i];
+  __syncthreads();
+  fft_lines<W, RB, +1, kNTB, 1, LD>(z, tw, tid);
+  const float* u0 = u ? u + (size_t)p * 2 * N : nullptr;
+  float* n0 = unext + (size_t)p * 2 * N + (size_t)row0 * W;
+  float* v0 = vout ? vout + (size_t)p * 2 * N + (size_t)row0 * W : nullptr;
+  for (int i = tid; i < RB * W; i += kNTB) {
+    const int rr = i / W, c = i % W, r = row0 + rr;
+    const float2 v = z[rr * LD + c];
+    float a = mdt * v.x, b = mdt * v.y;
+    if (u0) {
+      const Taps t = make_taps<BG>((float)r + a, (float)c + b, H, W);
+      a += tap_sample<BG>(t, u0[t.o00], u0[t.o10], u0[t.o01], u0[t.o11]);
+      b += tap_sample<BG>(t, u0[N + t.o00], u0[N + t.o10], u0[N + t.o01], u0[N + t.o11]);
+    }
+    n0[i] = a;
+    n0[N + i] = b;
+    if (v0) { v0[i] = v.x; v0[N + i] = v.y; }
+  }
+}
+
+template <int H, int W>
+static int big_step(const float* u, const float* m0, float* unext, float* vout, float2* zg, int64_t P,
+                    FluidParams fp, float mdt, int bg, cudaStream_t st) {
+  constexpr int N1w = Fact<W>::N1, N2w = Fact<W>::N2, RB = kBandRows;
+  static_assert(H % RB == 0 && H % kRowsPerCta == 0, "row bands must divide H");
+  const size_t smem_fft = sizeof(float2) * ((size_t)kRowsPerCta * (W + 1) + W);
+  const size_t smem_ad = sizeof(float2) * ((size_t)RB * (W + 1) + W + (size_t)(RB + 2) * W);
+  const size_t smem_co = sizeof(float2) * ((size_t)RB * (W + 1) + W);
+  const size_t smem_cols = sizeof(float2) * ((size_t)H * (2 * N2w + 1) + 2 * H + W);
+  for (int64_t p0 = 0; p0 < P; p0 += kMaxGridY) {
+    const unsigned pn = (unsigned)((P - p0 < kMaxGridY) ? P - p0 : kMaxGridY);
+    const size_t foff = (size_t)p0 * 2 * H * W;
+    float2* zp0 = zg + (size_t)p0 * H * W;
+    if (u) {
+      if (bg == B2_BG_CLAMP) {
+        B2_CUDA(cudaFuncSetAttribute(adstar_rows_kernel<W, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ad));
+        adstar_rows_kernel<W, B2_BG_CLAMP><<<dim3(H / RB, pn), kNTB, smem_ad, st>>>(u + foff, m0 + foff, zp0, H);
+      } else {
+        B2_CUDA(cudaFuncSetAttribute(adstar_rows_kernel<W, B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ad));
+        adstar_rows_kernel<W, B2_BG_ZERO><<<dim3(H / RB, pn), kNTB, smem_ad, st>>>(u + foff, m0 + foff, zp0, H);
+      }
+    } else {   // u = 0: Ad* is the identity, m = m0
+      B2_CUDA(cudaFuncSetAttribute(fft_rows_kernel<W, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+      fft_rows_kernel<W, -1><<<dim3(H / kRowsPerCta, pn), kNTB, smem_fft, st>>>(m0 + foff, zp0, nullptr, H);
+    }
+    B2_CHECK_LAUNCH();
+    B2_CUDA(cudaFuncSetAttribute(fft_cols_kernel<H, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    fft_cols_kernel<H, W, true><<<dim3(N1w / 2 + 1, pn), kNTB, smem_cols, st>>>(zp0, fp);
+    B2_CHECK_LAUNCH();
+    if (bg == B2_BG_CLAMP) {
+      B2_CUDA(cudaFuncSetAttribute(compose_rows_kernel<W, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_co));
+      compose_rows_kernel<W, B2_BG_CLAMP><<<dim3(H / RB, pn), kNTB, smem_co, st>>>(zp0, u ? u + foff : nullptr, unext + foff, vout ? vout + foff : nullptr, H, mdt);
+    } else {
+      B2_CUDA(cudaFuncSetAttribute(compose_rows_kernel<W, B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_co));
+      compose_rows_kernel<W, B2_BG_ZERO><<<dim3(H / RB, pn), kNTB, smem_co, st>>>(zp0, u ? u + foff : nullptr, unext + foff, vout ? vout + foff : nullptr, H, mdt);
+    }
+    B2_CHECK_LAUNCH();
+  }
+  return B2_OK;
+}
+
 static bool smem_path(int64_t H, int64_t W) { return H == W && (H == 16 || H == 32 || H == 64 || H == 128); }
 static bool pass3_path(int64_t H, int64_t W) {
   return (H == 256 && W == 256) || (H == 64 && W == 128) || (H == 128 && W == 64) || (H == 256 && W == 128) ||
@@ -210,6 +331,20 @@ int fluid_apply_impl(const float* f, float* out, int64_t P, int64_t H, int64_t W
     if (H == 256 && W == 128) return launch_3pass<256, 128>(f, out, P, fp, inverse, zg, st);
     if (H == 128 && W == 256) return launch_3pass<128, 256>(f, out, P, fp, inverse, zg, st);
   }
+  return B2_E_FFTSIZE;
+}
+
+// One EPDiff step on the big-grid path: unext = compose(u, sharp(Ad*_u m0), -dt); u == nullptr means u = 0.
+// vout (optional) receives v = sharp(Ad*_u m0).  zg: P*H*W float2 scratch.
+int epdiff_step_big(const float* u, const float* m0, float* unext, float* vout, void* zg, int64_t P, int64_t H,
+                    int64_t W, float alpha, float beta, float gamma, float dt, int bg, cudaStream_t st) {
+  FluidParams fp{alpha, beta, gamma, 1.0f / (float)(H * W)};
+  float2* z = reinterpret_cast<float2*>(zg);
+  if (H == 256 && W == 256) return big_step<256, 256>(u, m0, unext, vout, z, P, fp, -dt, bg, st);
+  if (H == 64 && W == 128) return big_step<64, 128>(u, m0, unext, vout, z, P, fp, -dt, bg, st);
+  if (H == 128 && W == 64) return big_step<128, 64>(u, m0, unext, vout, z, P, fp, -dt, bg, st);
+  if (H == 256 && W == 128) return big_step<256, 128>(u, m0, unext, vout, z, P, fp, -dt, bg, st);
+  if (H == 128 && W == 256) return big_step<128, 256>(u, m0, unext, vout, z, P, fp, -dt, bg, st);
   return B2_E_FFTSIZE;
 }
 

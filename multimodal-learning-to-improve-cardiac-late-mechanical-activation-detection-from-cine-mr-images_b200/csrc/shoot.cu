@@ -29,6 +29,9 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
                     int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st,
                     const float* du_add);
 
+int epdiff_step_big(const float* u, const float* m0, float* unext, float* vout, void* zg, int64_t P, int64_t H,
+                    int64_t W, float alpha, float beta, float gamma, float dt, int bg, cudaStream_t st);
+
 constexpr int kFusedMaxSectors = 256;
 #ifndef B2_FAST_GATHER
 #define B2_FAST_GATHER 0
@@ -348,7 +351,7 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
     m0 = m0w;
   }
   float* uscr = reinterpret_cast<float*>(ws + fbytes);
-  float* mv = reinterpret_cast<float*>(ws + 2 * fbytes);
+  (void)fbytes;
   void* fws = ws + 3 * fbytes;
   const int64_t fws_bytes = b2_fluid_workspace_bytes(P, H, W);
   const int S = a.num_steps;
@@ -356,22 +359,17 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   const size_t n = (size_t)P * field;
   const float* ucur = nullptr;
   for (int s = 0; s < S; ++s) {
-    float* vbuf = a.traj ? a.traj + (size_t)(s * 2 + 1) * n : mv;
-    if (s == 0) {
-      if (int e = fluid_apply_impl(m0, vbuf, P, H, W, a.alpha, a.beta, a.gamma, 1, fws, fws_bytes, st)) return e;
-      if (a.vel) B2_CUDA(cudaMemcpyAsync(a.vel, vbuf, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-      if (a.traj) B2_CUDA(cudaMemsetAsync(a.traj, 0, sizeof(float) * n, st));
-    } else {
-      if (int e = b2_adstar_fwd(ucur, m0, vbuf, P, H, W, a.background, stream)) return e;
-      if (int e = fluid_apply_impl(vbuf, vbuf, P, H, W, a.alpha, a.beta, a.gamma, 1, fws, fws_bytes, st)) return e;
-    }
+    // v_s goes to the trajectory (training), to `vel` at s = 0, or nowhere; m/v stay out of HBM otherwise
+    float* vout = a.traj ? a.traj + (size_t)(s * 2 + 1) * n : ((s == 0 && a.vel) ? a.vel : nullptr);
     float* unext;
     if (a.traj) unext = (s + 1 < S) ? a.traj + (size_t)((s + 1) * 2) * n : a.u;
     else unext = (((S - (s + 1)) & 1) == 0) ? a.u : uscr;
+    if (int e = epdiff_step_big(ucur, m0, unext, vout, fws, P, H, W, a.alpha, a.beta, a.gamma, dt, a.background, st)) return e;
     if (s == 0) {
-      if (int e = axpby(unext, vbuf, -dt, 0.f, n, st)) return e;
-    } else {
-      if (int e = b2_compose_fwd(ucur, vbuf, unext, P, H, W, -dt, a.background, stream)) return e;
+      if (a.traj) {
+        B2_CUDA(cudaMemsetAsync(a.traj, 0, sizeof(float) * n, st));
+        if (a.vel) B2_CUDA(cudaMemcpyAsync(a.vel, vout, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+      }
     }
     ucur = unext;
   }
