@@ -112,7 +112,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv is not None:

@@ -240,7 +240,8 @@ def test_strain_matrix(pkg, oracle, dev, n_frames):
               lambda a: oracle.strain_matrix(a, tar, mask0, n_frames=n_frames), [u])
 
 
-@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 3), (2, 5, 64, 64, 10), (1, 3, 128, 128, 10), (1, 3, 256, 256, 2)])
+@pytest.mark.parametrize("cfg", [(3, 3, 16, 16, 3), (2, 4, 32, 32, 3), (2, 5, 64, 64, 10), (1, 3, 128, 128, 10),
+                                 (1, 3, 256, 256, 2), (2, 3, 64, 128, 3), (1, 3, 128, 256, 2)])
 def test_forward_volume_parity(pkg, oracle, dev, cfg):
     """The fused kernel (and the op-level path for 256^2) vs the oracle, all outputs."""
     B, T, H, W, S = cfg
