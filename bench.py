@@ -127,6 +127,25 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs local to its GPU before any pinned host memory is allocated, so the staging
+    buffers are first-touched on the GPU's NUMA node (matters for the host->device leg at N >= 4)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def make_inputs(pkg, n_slices, seed):
     vol = pkg.synthetic.synthetic_masks(n_slices, T_FRAMES, H, W, seed=seed)                  # (B,1,T,H,W)
     v0 = pkg.synthetic.synthetic_v0(n_slices * (T_FRAMES - 1), H, W, seed=seed + 1, max_disp=3.0)
@@ -200,6 +219,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
