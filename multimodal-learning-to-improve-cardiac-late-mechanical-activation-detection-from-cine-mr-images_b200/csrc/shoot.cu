@@ -49,7 +49,7 @@ template <int H, int W>
 struct ShootSmem {
   using FS = FluidSmem<H, W>;
   static constexpr size_t bins_off = (FS::bytes + 15) & ~size_t(15);
-  static constexpr size_t bytes = bins_off + sizeof(int32_t) * 4 * kFusedMaxSectors;
+  static constexpr size_t bytes = bins_off + sizeof(int32_t) * 5 * kFusedMaxSectors;
 };
 
 // Thread <-> pixel map of every per-pixel phase: a thread keeps ONE column c = tid % W and walks the
@@ -64,11 +64,11 @@ shoot_fwd_kernel(const ShootParams prm) {
   constexpr int LD = FS::LD, N = H * W, RB = NT / W, NB = H / RB;
   float2 *z, *twH, *twW, *csH, *csW;
   FS::carve(smem_raw, z, twH, twW, csH, csW);
-  int32_t* tab_s = reinterpret_cast<int32_t*>(smem_raw + ShootSmem<H, W>::bins_off);
   const b2_shoot_args& a = prm.a;
   const int n_sectors = a.n_sectors;
-  float* sums_s = reinterpret_cast<float*>(tab_s + 2 * n_sectors);
-  int* cnts_s = tab_s + 3 * n_sectors;
+  unsigned long long* sums_s = reinterpret_cast<unsigned long long*>(smem_raw + ShootSmem<H, W>::bins_off);
+  int32_t* tab_s = reinterpret_cast<int32_t*>(sums_s + n_sectors);
+  int* cnts_s = tab_s + 2 * n_sectors;
   const int tid = threadIdx.x;
   const int c = tid % W, br = tid / W;
   const int S = a.num_steps;
@@ -209,7 +209,7 @@ shoot_fwd_kernel(const ShootParams prm) {
     }
     // ---- strain matrix column t of slice b
     if (a.S) {
-      for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0.f; cnts_s[i] = 0; }
+      for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0ull; cnts_s[i] = 0; }
       __syncthreads();
       const float* tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N
                                              : a.tar + (size_t)p * N;

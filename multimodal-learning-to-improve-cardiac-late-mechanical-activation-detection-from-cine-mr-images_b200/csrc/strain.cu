@@ -51,17 +51,17 @@ __global__ void __launch_bounds__(kNTS)
 strain_sector_fwd_kernel(const float* __restrict__ u, const float* __restrict__ tar, const long long* __restrict__ mom,
                          const int32_t* __restrict__ table, float* __restrict__ S, int32_t* __restrict__ counts,
                          int B, int T1, int H, int W, int n_sectors, int n_frames) {
-  extern __shared__ int32_t smem_i[];
-  int32_t* tab_s = smem_i;
-  float* sums_s = reinterpret_cast<float*>(smem_i + 2 * n_sectors);
-  int* cnts_s = smem_i + 3 * n_sectors;
+  extern __shared__ __align__(8) unsigned long long smem_q[];
+  unsigned long long* sums_s = smem_q;                                   // n_sectors x u64
+  int32_t* tab_s = reinterpret_cast<int32_t*>(smem_q + n_sectors);       // 2 n_sectors x i32
+  int* cnts_s = tab_s + 2 * n_sectors;                                   // n_sectors x i32
   const int tid = threadIdx.x;
   const int N = H * W;
   for (int i = tid; i < 2 * n_sectors; i += kNTS) tab_s[i] = table[i];
   for (long long pt = blockIdx.x; pt < (long long)B * T1; pt += gridDim.x) {
     const int b = (int)(pt / T1), t = (int)(pt % T1);
     __syncthreads();
-    for (int i = tid; i < n_sectors; i += kNTS) { sums_s[i] = 0.f; cnts_s[i] = 0; }
+    for (int i = tid; i < n_sectors; i += kNTS) { sums_s[i] = 0ull; cnts_s[i] = 0; }
     __syncthreads();
     const float* u0 = u + (size_t)pt * 2 * N;
     strain_bin_frame<kNTS>(u0, u0 + N, tar + (size_t)pt * N, mom + 3 * b, tab_s, n_sectors, H, W, sums_s, cnts_s, tid);
@@ -208,7 +208,7 @@ extern "C" int b2_strain_sector_fwd(const float* u, const float* tar, const int6
   cudaStream_t st = (cudaStream_t)stream;
   int64_t grid = B * T1;
   if (grid > (1 << 20)) grid = 1 << 20;
-  strain_sector_fwd_kernel<<<(unsigned)grid, kNTS, sizeof(int32_t) * 4 * n_sectors, st>>>(
+  strain_sector_fwd_kernel<<<(unsigned)grid, kNTS, sizeof(int32_t) * 5 * n_sectors, st>>>(
       u, tar, reinterpret_cast<const long long*>(moments), table, S, counts, (int)B, (int)T1, (int)H, (int)W,
       n_sectors, n_frames);
   B2_CHECK_LAUNCH();

@@ -7,13 +7,26 @@ namespace b2 {
 
 constexpr int kMaxSectors = 1024;
 
+// Sector sums are accumulated in Q31.32 fixed point with 64-bit integer shared-memory atomics: integer
+// addition is associative, so the strain matrix is bit-identical run to run regardless of the order in
+// which threads arrive (float atomics are not).  Quantisation 2^-32 per pixel is far below fp32 resolution.
+constexpr float kFixScale = 4294967296.0f;            // 2^32
+constexpr double kFixInv = 1.0 / 4294967296.0;
+__device__ __forceinline__ unsigned long long ecc_to_fixed(float ecc) {
+  const float lim = 1.0e9f;                            // |Ecc| beyond 1e9 is saturated (degenerate Jacobian)
+  return (unsigned long long)__float2ll_rn(fminf(fmaxf(ecc, -lim), lim) * kFixScale);
+}
+__device__ __forceinline__ float fixed_to_mean(unsigned long long s, int cnt) {
+  return (float)((double)(long long)s * kFixInv / (double)max(cnt, 1));
+}
+
 // Accumulate one (slice, frame) into shared-memory bins.  `u0/u1` point at the
 // displacement of this pair, `mask` at its target-frame mask; all threads of the
 // CTA call this; bins must be zeroed + synced before and are synced after.
 template <int NT>
 __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u1, const float* __restrict__ mask,
                                                  const long long* mom, const int32_t* tab_s, int n_sectors,
-                                                 int H, int W, float* sums_s, int* cnts_s, int tid) {
+                                                 int H, int W, unsigned long long* sums_s, int* cnts_s, int tid) {
   const long long cnt = mom[0], sx = mom[1], sy = mom[2];
   float c0, c1;
   centroid_from_moments(mom, H, W, c0, c1);
@@ -32,7 +45,7 @@ __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u
     const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
     EccTerms e; float ecc;
     if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[x], (float)c + u1[x], c0, c1, e, ecc)) continue;
-    atomicAdd(&sums_s[k], ecc);
+    atomicAdd(&sums_s[k], ecc_to_fixed(ecc));
     atomicAdd(&cnts_s[k], 1);
   }
   __syncthreads();
@@ -41,12 +54,12 @@ __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u
 // Write column t of S (B,1,K,n_frames) from the bins, with edge-padding of the
 // last frame and cropping beyond n_frames (align_n_frames_to semantics).
 template <int NT>
-__device__ __forceinline__ void strain_store_column(const float* sums_s, const int* cnts_s, float* __restrict__ S,
+__device__ __forceinline__ void strain_store_column(const unsigned long long* sums_s, const int* cnts_s, float* __restrict__ S,
                                                     int32_t* __restrict__ counts, int b, int t, int T1,
                                                     int n_sectors, int n_frames, int tid) {
   for (int k = tid; k < n_sectors; k += NT) {
     const int cn = cnts_s[k];
-    const float v = sums_s[k] / (float)max(cn, 1);
+    const float v = fixed_to_mean(sums_s[k], cn);
     float* row = S + ((size_t)b * n_sectors + k) * n_frames;
     if (t < n_frames) row[t] = v;
     if (t == T1 - 1)

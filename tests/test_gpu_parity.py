@@ -331,16 +331,14 @@ def test_host_pipeline_matches_resident(pkg, dev):
     ref = pkg.shoot_warp_strain(v0.to(dev), sv, tv, metric, num_steps=S)           # strided views, in place
     ref_c = pkg.shoot_warp_strain(v0.to(dev), sv.contiguous(), tv.contiguous(), metric, num_steps=S)
     got = pipe.result()
-    for k in ("momentum", "velocity", "displacement", "deformed_source"):
+    # every output is bit-identical: the sector sums use fixed-point integer atomics (order independent)
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
         assert torch.equal(got[k], ref[k]), k
         assert torch.equal(ref[k], ref_c[k]), k
-    # sector sums are accumulated with shared-memory float atomics: order (hence the last bits) may differ
-    assert relerr(got["strain_matrix"], ref["strain_matrix"]) < 1e-6
-    assert relerr(ref_c["strain_matrix"], ref["strain_matrix"]) < 1e-6
-    assert relerr(S_host, ref["strain_matrix"]) < 1e-6
+    assert torch.equal(S_host, ref["strain_matrix"].cpu())
     S2 = pipe(v0, vol)                                                       # reusable
     torch.cuda.synchronize()
-    assert relerr(S2, ref["strain_matrix"]) < 1e-6
+    assert torch.equal(S2, ref["strain_matrix"].cpu())
 
 
 def test_full_size_properties(pkg, dev):
@@ -362,6 +360,8 @@ def test_full_size_properties(pkg, dev):
     # idempotence / determinism of everything that has no float atomics
     again = pkg.shoot_warp_strain(v0, src_vol.to(dev), tar_vol.to(dev), metric, num_steps=S)
     assert torch.equal(again["displacement"], out["displacement"])
+    assert torch.equal(again["strain_matrix"], out["strain_matrix"])    # fixed-point sector sums: reproducible
+    assert torch.equal(sub["strain_matrix"], out["strain_matrix"][:4])
     # warped binary masks stay in [0,1]; zero velocity is the identity map
     assert out["deformed_source"].min() >= 0 and out["deformed_source"].max() <= 1
     ident = pkg.shoot_warp_strain(torch.zeros_like(v0[:24]), src_vol[:1].to(dev), tar_vol[:1].to(dev), metric, num_steps=S)
