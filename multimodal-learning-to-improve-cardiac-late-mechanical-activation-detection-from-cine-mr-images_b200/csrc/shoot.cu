@@ -37,6 +37,10 @@ constexpr int kFusedMaxSectors = 256;
 #define B2_FAST_GATHER 0
 #endif
 constexpr bool kFastGather = B2_FAST_GATHER != 0;
+#ifndef B2_COMPOSE_UNROLL
+#define B2_COMPOSE_UNROLL 2
+#endif
+constexpr int kComposeUnroll = B2_COMPOSE_UNROLL;
 
 struct ShootParams {
   b2_shoot_args a;
@@ -124,7 +128,10 @@ shoot_fwd_kernel(const ShootParams prm) {
       // Band k is overwritten with m only after every thread has read it (one barrier per band); the
       // row above the next band is prefetched into a register before it is overwritten.
       if (s > 0) {
-        constexpr int G = NB < 4 ? NB : 4;       // bands per barrier: G pixels of m stay in registers
+#ifndef B2_ADSTAR_G
+#define B2_ADSTAR_G 16
+#endif
+        constexpr int G = NB < B2_ADSTAR_G ? NB : B2_ADSTAR_G;   // bands per barrier: G pixels of m stay in registers
         float2 up_saved = make_float2(0.f, 0.f);
         for (int g = 0; g < NB / G; ++g) {
           float2 m[G];
@@ -177,7 +184,7 @@ shoot_fwd_kernel(const ShootParams prm) {
           if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
         }
       } else {
-#pragma unroll 2
+#pragma unroll (kComposeUnroll)
         for (int k = 0; k < NB; ++k) {
           const int r = k * RB + br, i = r * W + c;
           const float2 v = z[r * LD + c];
