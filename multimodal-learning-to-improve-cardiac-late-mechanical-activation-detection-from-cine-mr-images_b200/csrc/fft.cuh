@@ -171,6 +171,11 @@ __device__ __forceinline__ void init_symbol_lut(float2* cs, int tid, int nthread
 
 struct FluidParams { float alpha, beta, gamma, scale; };
 
+#ifndef B2_MULT_UNROLL
+#define B2_MULT_UNROLL 2
+#endif
+constexpr int kMultUnroll = B2_MULT_UNROLL;
+
 // A, B of W = A Z + B conj(Z~) at frequency (k0, k1)
 template <bool INVERSE>
 __device__ __forceinline__ void fluid_coeffs(const FluidParams& fp, float2 cs0, float2 cs1,
@@ -207,6 +212,7 @@ __device__ __forceinline__ void fluid_multiply(float2* __restrict__ z, const flo
   const float2 cs1 = csW[k1];
   const float h = 0.5f * fp.scale;
   const float bs1 = fp.beta * cs1.y;
+#pragma unroll (kMultUnroll)
   for (int k0 = br; k0 <= H / 2; k0 += RB) {
     const int pr = freq_to_cell<H>(k0), qr = freq_to_cell<H>((H - k0) & (H - 1));
     if (pr == qr && pc > qc) continue;          // self-mirrored rows (k0 = 0, H/2): each pair once

@@ -10,6 +10,12 @@
 namespace b2 {
 
 constexpr int kThreads = 256;
+#ifndef B2_PAIRS_PER_THREAD
+#define B2_PAIRS_PER_THREAD 1
+#endif
+// with kPairsPerThread > 1 every thread walks several pairs (stride gridDim.y) in an unrolled loop, which puts
+// that many independent load chains in flight per thread
+constexpr int kPairsPerThread = B2_PAIRS_PER_THREAD;
 
 // pixel -> (row, col); W is a power of two for every FFT-sized grid, so the common case is a shift
 __device__ __forceinline__ void row_col(int x, int W, int wshift, int& r, int& c) {
@@ -29,6 +35,7 @@ interp_fwd_kernel(const float* __restrict__ I, const float* __restrict__ u, floa
   int r, c;
   row_col(x, W, wshift, r, c);
   const int nc = CT ? CT : C;
+#pragma unroll (kPairsPerThread)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* up = u + (size_t)(p * su) * 2 * N + x;
     const float u0 = up[0], u1 = up[N];
@@ -60,6 +67,7 @@ interp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ I, c
   int r, c;
   row_col(x, W, wshift, r, c);
   const int nc = CT ? CT : C;
+#pragma unroll (kPairsPerThread)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* up = u + (size_t)(p * su) * 2 * N + x;
     const float u0 = up[0], u1 = up[N];
@@ -117,6 +125,7 @@ splat_fwd_kernel(const float* __restrict__ J, const float* __restrict__ u, float
   int r, c;
   row_col(x, W, wshift, r, c);
   const int nc = CT ? CT : C;
+#pragma unroll (kPairsPerThread)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* up = u + (size_t)(p * su) * 2 * N + x;
     const Taps t = make_taps<BG>((float)r + dt * up[0], (float)c + dt * up[N], H, W);
@@ -162,7 +171,8 @@ static int check_dims(int64_t P, int64_t PI, int64_t Pu, int64_t C, int64_t H, i
 }
 
 static dim3 pixel_grid(int64_t P, int64_t N) {
-  return dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)(P < kMaxGridY ? P : kMaxGridY), 1);
+  int64_t gy = (P + kPairsPerThread - 1) / kPairsPerThread;
+  return dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)(gy < kMaxGridY ? gy : kMaxGridY), 1);
 }
 
 template <bool ADD_U>

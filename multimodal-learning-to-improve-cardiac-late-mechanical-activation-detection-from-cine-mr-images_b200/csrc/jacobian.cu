@@ -9,6 +9,10 @@
 namespace b2 {
 
 constexpr int kThreadsJ = 256;
+#ifndef B2_PAIRS_PER_THREAD
+#define B2_PAIRS_PER_THREAD 1
+#endif
+constexpr int kPairsPerThreadJ = B2_PAIRS_PER_THREAD;
 
 struct Jac { float d00, d01, d10, d11; };   // d_ab = d v_a / d x_b
 
@@ -33,6 +37,7 @@ jtv_fwd_kernel(const float* __restrict__ v, const float* __restrict__ w, float* 
   const int x = blockIdx.x * kThreadsJ + threadIdx.x;
   if (x >= N) return;
   const int r = x / W, c = x - r * W;
+#pragma unroll (kPairsPerThreadJ)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* vp = v + (size_t)p * 2 * N;
     const float* wp = w + (size_t)p * 2 * N;
@@ -65,6 +70,7 @@ jtv_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const f
   const int x = blockIdx.x * kThreadsJ + threadIdx.x;
   if (x >= N) return;
   const int r = x / W, c = x - r * W;
+#pragma unroll (kPairsPerThreadJ)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* vp = v + (size_t)p * 2 * N;
     const float* wp = w + (size_t)p * 2 * N;
@@ -123,6 +129,7 @@ adstar_fwd_kernel(const float* __restrict__ u, const float* __restrict__ m0, flo
   diff_idx(r, H, rlo, rhi, sr);
   diff_idx(c, W, clo, chi, sc);
   const int oup = rlo * W + c, odn = rhi * W + c, olf = r * W + clo, ort = r * W + chi;
+#pragma unroll (kPairsPerThreadJ)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* u0 = u + (size_t)p * 2 * N;
     const float* u1 = u0 + N;
@@ -161,6 +168,7 @@ adstar_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, cons
   const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
   const float cmc = (c >= 1) ? diff_scale(c - 1, W) : 0.f, cpc = (c <= W - 2) ? diff_scale(c + 1, W) : 0.f;
   const float c0c = (c == W - 1 ? 1.f : 0.f) - (c == 0 ? 1.f : 0.f);
+#pragma unroll (kPairsPerThreadJ)
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* u0 = u + (size_t)p * 2 * N;
     const float* u1 = u0 + N;
@@ -226,7 +234,8 @@ static int check_pf(int64_t P, int64_t H, int64_t W) {
   return B2_OK;
 }
 static dim3 pgrid(int64_t P, int64_t N) {
-  return dim3((unsigned)((N + kThreadsJ - 1) / kThreadsJ), (unsigned)(P < kMaxGridY ? P : kMaxGridY), 1);
+  int64_t gy = (P + kPairsPerThreadJ - 1) / kPairsPerThreadJ;
+  return dim3((unsigned)((N + kThreadsJ - 1) / kThreadsJ), (unsigned)(gy < kMaxGridY ? gy : kMaxGridY), 1);
 }
 
 }  // namespace b2
