@@ -152,7 +152,8 @@ typedef struct b2_shoot_args {
   int32_t* counts;
   float* traj;
   int64_t B, T1, H, W;
-  int64_t src_slice_stride;  /* elements between the source images of consecutive slices; 0 = H*W */
+  int64_t src_slice_stride;  /* elements between the (first) source images of consecutive slices; 0 = dense.
+                                With src_per_pair the source of pair (b,t) is src + b*stride + t*H*W. */
   int64_t tar_slice_stride;  /* elements between the first target frames of consecutive slices; 0 = T1*H*W.
                                 With both set to T*H*W, src = vol and tar = vol + H*W read a (B,1,T,H,W) cine
                                 volume in place: no pair construction, no copies (fused path only). */

@@ -204,8 +204,12 @@ shoot_fwd_kernel(const ShootParams prm) {
 
     // ---- deformed_source = interp(src, u^S)
     if (a.sdef) {
-      const float* src = a.src_per_pair ? a.src + (size_t)p * N
-                                        : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
+      // Lagrangian split: one source image per slice; Eulerian split (src_per_pair): one per pair, either
+      // dense (P,1,H,W) or frames of a strided cine volume (slice stride given)
+      const float* src = a.src_per_pair
+                             ? (a.src_slice_stride ? a.src + (size_t)b * a.src_slice_stride + (size_t)t * N
+                                                   : a.src + (size_t)p * N)
+                             : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
       float* sd = a.sdef + (size_t)p * N;
 #pragma unroll 2
       for (int k = 0; k < NB; ++k) {

@@ -84,8 +84,9 @@ class JointRegisterStrainMatNet(nn.Module):
     def forward_volume(self, src_vol, tar_vol):
         """src_vol, tar_vol (B,1,T-1,H,W) -> {'strain_matrix','deformed_source','velocity','momentum',...}."""
         B, C, T1, H, W = tar_vol.shape
-        src0 = src_vol[:, :, :1].expand(B, C, T1, H, W)
-        v0 = self.velocity_net(src0.reshape(B * T1, C, H, W), tar_vol.reshape(B * T1, C, H, W))
+        # pair (b, t) registers src_vol[b, :, t] to tar_vol[b, :, t]: frame 0 for every t under the Lagrangian
+        # split, frame t under the Eulerian one (modules/data/__init__.py:108-113)
+        v0 = self.velocity_net(src_vol.reshape(B * T1, C, H, W), tar_vol.reshape(B * T1, C, H, W))
         out = shoot_warp_strain(v0, src_vol, tar_vol, self.metric, self.num_steps,
                                 n_sectors=self.n_sectors, n_frames=self.n_strain_matrix_frames)
         if self.smoothing == "SVD":

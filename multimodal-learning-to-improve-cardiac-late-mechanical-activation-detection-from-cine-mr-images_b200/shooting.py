@@ -172,7 +172,8 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         m0, u, traj, src, tar, moments, table, counts = ctx.saved_tensors
         metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain = ctx.cfg
         P, _, H, W = m0.shape
-        src_c = src.contiguous()                       # op-level adjoint kernels take dense batches
+        # op-level adjoint kernels take dense batches
+        src_c = src.reshape(P, 1, H, W).contiguous() if src_per_pair else src.contiguous()
         gu_tot = gu.contiguous().clone() if gu is not None else torch.zeros_like(u)
         dsrc = None
         if gsdef is not None:
@@ -224,20 +225,28 @@ def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T
     B, Cc, T1, H, W = tar_vol.shape
     if Cc != 1 or v0.shape != (B * T1, 2, H, W):
         raise _lib.B2Error(f"shape mismatch: v0 {tuple(v0.shape)}, tar_vol {tuple(tar_vol.shape)}")
-    src = src_vol[:, :, 0]                                     # (B,1,H,W) frame-0 mask (view)
+    if tuple(src_vol.shape) != (B, Cc, T1, H, W):
+        raise _lib.B2Error(f"shape mismatch: src_vol {tuple(src_vol.shape)}, tar_vol {tuple(tar_vol.shape)}")
+    mask0 = src_vol[:, 0, 0]                                   # frame-0 mask: centroid + sectors of the slice
+    # Lagrangian split (modules/data/__init__.py:108-110): every pair of a slice shares frame 0 - an expanded
+    # view has frame stride 0.  Otherwise (Eulerian split, or a materialised repeat) each pair has its own source.
+    shared = T1 == 1 or src_vol.stride(2) == 0
+    src = src_vol[:, :, 0] if shared else src_vol
     src_ss = tar_ss = 0
-    if _fused_size(H, W) and _rows_dense(src) and _rows_dense(tar_vol) and tar_vol.stride(2) == H * W:
-        src_ss = src.stride(0) if B > 1 else H * W
+    strided_ok = (_fused_size(H, W) and _rows_dense(src) and _rows_dense(tar_vol) and tar_vol.stride(2) == H * W
+                  and (shared or src_vol.stride(2) == H * W))
+    if strided_ok:
+        src_ss = src.stride(0) if B > 1 else T1 * H * W
         tar_ss = tar_vol.stride(0) if B > 1 else T1 * H * W
         tar = tar_vol
     else:
-        src = src.contiguous()
+        src = src.contiguous() if shared else src_vol.reshape(B * T1, 1, H, W).contiguous()
         tar = tar_vol.reshape(B * T1, 1, H, W).contiguous()
-    moments = mask_moments(src[:, 0].contiguous()) if with_strain else None
+    moments = mask_moments(mask0.contiguous()) if with_strain else None
     table = sector_table(n_sectors, v0.device) if with_strain else None
     m0, vel, u, sdef, S = ShootWarpStrainFunction.apply(
         v0, src, tar, moments, table, metric, int(num_steps), float(T), BG[background], int(n_sectors),
-        int(n_frames), B, T1, False, bool(with_strain), int(src_ss), int(tar_ss))
+        int(n_frames), B, T1, not shared, bool(with_strain), int(src_ss), int(tar_ss))
     return {
         "strain_matrix": S,
         "deformed_source": sdef.reshape(B, 1, T1, H, W),
