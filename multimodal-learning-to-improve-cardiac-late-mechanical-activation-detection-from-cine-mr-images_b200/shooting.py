@@ -285,7 +285,7 @@ class HostPipeline:
         dev, T1, cs = self.dev, self.T1, self.chunk
         self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
                        "v0": torch.empty((cs * T1, 2, H, W), device=dev),
-                       "ready": torch.cuda.Event(), "free": torch.cuda.Event()} for _ in range(2)]
+                       "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False} for _ in range(2)]
         P = B * T1
         self.out = _alloc_outputs(P, B, T1, H, W, dev, {"m0": True, "vel": True, "sdef": True, "S": True}, False,
                                   self.n_sectors, self.n_frames, self.num_steps, False)
@@ -306,8 +306,8 @@ class HostPipeline:
                 nb = b1 - b0
                 st = self.stage[i % 2]
                 with torch.cuda.stream(self.copy_stream):
-                    if i >= 2:
-                        self.copy_stream.wait_event(st["free"])          # kernel of chunk i-2 done with this stage
+                    if st["used"]:                                       # last kernel that read this stage is done
+                        self.copy_stream.wait_event(st["free"])          # (also across consecutive calls)
                     st["vol"][:nb].copy_(vol_host[b0:b1], non_blocking=True)
                     st["v0"][: nb * T1].copy_(v0_host[b0 * T1: b1 * T1], non_blocking=True)
                     st["ready"].record(self.copy_stream)
@@ -322,6 +322,7 @@ class HostPipeline:
                               {}, False, False, False, out=out, ws=self.ws,
                               src_slice_stride=T * H * W, tar_slice_stride=T * H * W)
                 st["free"].record(main)
+                st["used"] = True
                 self.S_host[b0:b1].copy_(self.out["S"][b0:b1], non_blocking=True)
         return self.S_host
 
