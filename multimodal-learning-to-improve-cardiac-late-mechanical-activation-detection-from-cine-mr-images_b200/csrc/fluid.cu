@@ -70,8 +70,15 @@ static int launch_smem(const float* f, float* out, int64_t P, FluidParams fp, in
 }
 
 // ------------------------------------------------------------------ path B
-constexpr int kRowsPerCta = 32;
+#ifndef B2_FFT_ROWS
+#define B2_FFT_ROWS 32
+#endif
+#ifndef B2_COLS_NT
+#define B2_COLS_NT 256
+#endif
+constexpr int kRowsPerCta = B2_FFT_ROWS;
 constexpr int kNTB = 256;
+constexpr int kNTC = B2_COLS_NT;   // threads of the column kernel
 
 template <int W, int DIR>
 __global__ void __launch_bounds__(kNTB)
@@ -108,7 +115,7 @@ fft_rows_kernel(const float* __restrict__ f, float2* __restrict__ zg, float* __r
 
 // Column FFT + multiply + column IFFT on column-cell block j and its mirror block.
 template <int H, int W, bool INVERSE>
-__global__ void __launch_bounds__(kNTB)
+__global__ void __launch_bounds__(kNTC)
 fft_cols_kernel(float2* __restrict__ zg, FluidParams fp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N1w = Fact<W>::N1, N2w = Fact<W>::N2, NC = 2 * N2w, LD = NC + 1;
@@ -118,18 +125,18 @@ fft_cols_kernel(float2* __restrict__ zg, FluidParams fp) {
   float2* csW = csH + H;
   const int tid = threadIdx.x, p = blockIdx.y, j = blockIdx.x, jm = (N1w - j) % N1w;
   const bool self = (j == jm);
-  init_twiddles<H>(tw, tid, kNTB);
-  init_symbol_lut<H>(csH, tid, kNTB);
-  init_symbol_lut<W>(csW, tid, kNTB);
+  init_twiddles<H>(tw, tid, kNTC);
+  init_symbol_lut<H>(csH, tid, kNTC);
+  init_symbol_lut<W>(csW, tid, kNTC);
   float2* zp = zg + (size_t)p * H * W;
-  for (int i = tid; i < H * NC; i += kNTB) {
+  for (int i = tid; i < H * NC; i += kNTC) {
     const int r = i / NC, cc = i % NC;
     const int col = (cc < N2w) ? j * N2w + cc : jm * N2w + (cc - N2w);
     z[r * LD + cc] = zp[(size_t)r * W + col];
   }
   __syncthreads();
-  fft_lines<H, NC, -1, kNTB, LD, 1>(z, tw, tid);
-  for (int t = tid; t < H * N2w; t += kNTB) {
+  fft_lines<H, NC, -1, kNTC, LD, 1>(z, tw, tid);
+  for (int t = tid; t < H * N2w; t += kNTC) {
     const int pr = t / N2w, cc = t % N2w, pc = j * N2w + cc;
     const int k0 = cell_to_freq<H>(pr), k1 = cell_to_freq<W>(pc);
     const int qr = freq_to_cell<H>((H - k0) & (H - 1)), qc = freq_to_cell<W>((W - k1) & (W - 1));
@@ -145,9 +152,9 @@ fft_cols_kernel(float2* __restrict__ zg, FluidParams fp) {
       z[qr * LD + qcc] = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
   }
   __syncthreads();
-  fft_lines<H, NC, +1, kNTB, LD, 1>(z, tw, tid);
+  fft_lines<H, NC, +1, kNTC, LD, 1>(z, tw, tid);
   const int ncols = self ? N2w : NC;
-  for (int i = tid; i < H * NC; i += kNTB) {
+  for (int i = tid; i < H * NC; i += kNTC) {
     const int r = i / NC, cc = i % NC;
     if (cc >= ncols) continue;
     const int col = (cc < N2w) ? j * N2w + cc : jm * N2w + (cc - N2w);
@@ -172,10 +179,10 @@ static int launch_3pass(const float* f, float* out, int64_t P, FluidParams fp, i
     B2_CHECK_LAUNCH();
     if (inverse) {
       B2_CUDA(cudaFuncSetAttribute(fft_cols_kernel<H, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-      fft_cols_kernel<H, W, true><<<dim3(N1w / 2 + 1, (unsigned)pn), kNTB, smem_cols, st>>>(zp0, fp);
+      fft_cols_kernel<H, W, true><<<dim3(N1w / 2 + 1, (unsigned)pn), kNTC, smem_cols, st>>>(zp0, fp);
     } else {
       B2_CUDA(cudaFuncSetAttribute(fft_cols_kernel<H, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-      fft_cols_kernel<H, W, false><<<dim3(N1w / 2 + 1, (unsigned)pn), kNTB, smem_cols, st>>>(zp0, fp);
+      fft_cols_kernel<H, W, false><<<dim3(N1w / 2 + 1, (unsigned)pn), kNTC, smem_cols, st>>>(zp0, fp);
     }
     B2_CHECK_LAUNCH();
     fft_rows_kernel<W, +1><<<dim3(H / kRowsPerCta, (unsigned)pn), kNTB, smem_rows, st>>>(nullptr, zp0, op0, H);
@@ -191,10 +198,16 @@ static int launch_3pass(const float* f, float* out, int64_t P, FluidParams fp, i
 //   fft_cols_kernel    : column FFT + symbol multiply + column IFFT (above)
 //   compose_rows_kernel: row IFFT -> v, then u_next = interp(u, v, -dt) - dt v gathered from global
 // so m and v never round-trip through HBM (64*N instead of 96*N bytes per step).
-constexpr int kBandRows = 16;
+#ifndef B2_BAND_ROWS
+#define B2_BAND_ROWS 8
+#endif
+#ifndef B2_BAND_MINBLOCKS
+#define B2_BAND_MINBLOCKS 6
+#endif
+constexpr int kBandRows = B2_BAND_ROWS;
 
 template <int W, int BG>
-__global__ void __launch_bounds__(kNTB)
+__global__ void __launch_bounds__(kNTB, B2_BAND_MINBLOCKS)
 adstar_rows_kernel(const float* __restrict__ u, const float* __restrict__ m0, float2* __restrict__ zg, int H) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int LD = W + 1, RB = kBandRows;
@@ -232,7 +245,7 @@ adstar_rows_kernel(const float* __restrict__ u, const float* __restrict__ m0, fl
 }
 
 template <int W, int BG>
-__global__ void __launch_bounds__(kNTB)
+__global__ void __launch_bounds__(kNTB, B2_BAND_MINBLOCKS)
 compose_rows_kernel(const float2* __restrict__ zg, const float* __restrict__ u, float* __restrict__ unext,
                     float* __restrict__ vout, int H, float mdt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -291,7 +304,7 @@ static int big_step(const float* u, const float* m0, float* unext, float* vout, 
     }
     B2_CHECK_LAUNCH();
     B2_CUDA(cudaFuncSetAttribute(fft_cols_kernel<H, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    fft_cols_kernel<H, W, true><<<dim3(N1w / 2 + 1, pn), kNTB, smem_cols, st>>>(zp0, fp);
+    fft_cols_kernel<H, W, true><<<dim3(N1w / 2 + 1, pn), kNTC, smem_cols, st>>>(zp0, fp);
     B2_CHECK_LAUNCH();
     if (bg == B2_BG_CLAMP) {
       B2_CUDA(cudaFuncSetAttribute(compose_rows_kernel<W, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_co));
