@@ -387,12 +387,8 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   if (a.sdef) {
     if (a.src_per_pair) {
       if (int e = b2_interp_fwd(a.src, a.u, a.sdef, P, P, P, 1, H, W, 1.f, a.background, stream)) return e;
-    } else {
-      for (int64_t b = 0; b < a.B; ++b) {   // src broadcast over the T1 pairs of a slice
-        if (int e = b2_interp_fwd(a.src + (size_t)b * H * W, a.u + (size_t)b * a.T1 * field,
-                                  a.sdef + (size_t)b * a.T1 * H * W, a.T1, 1, a.T1, 1, H, W, 1.f, a.background, stream))
-          return e;
-      }
+    } else {   // one source image per slice, indexed in-kernel (no repeat)
+      if (int e = b2_warp_fwd(a.src, a.u, a.sdef, a.B, a.T1, 1, H, W, 1.f, a.background, stream)) return e;
     }
   }
   if (a.S) {

@@ -17,6 +17,8 @@ def pytest_configure(config):
 def pkg():
     """The product package (hyphenated directory name -> importlib)."""
     import __graft_entry__ as g
+    if not g.LIB.exists():          # fresh checkout: the shared library is git-ignored, build it once (nvcc, ~1-2 min)
+        g.build()
     return g.load_package()
 
 
