@@ -398,3 +398,62 @@ def test_full_size_properties(pkg, dev):
     assert ident["displacement"].abs().max() == 0
     assert torch.equal(ident["deformed_source"][0, 0, 0], src_vol[0, 0, 0].to(dev))
     assert ident["strain_matrix"].abs().max() < 1e-6               # (|e|^2/|e|^2 - 1)/2 up to fp32 rounding
+
+
+def test_c_abi_standalone(pkg, dev, tmp_path):
+    """The C ABI used WITHOUT torch (examples/c_abi_demo.cu: cudaMalloc + b2_* calls) gives bit-identical results
+    to the Python surface on the same inputs."""
+    import pathlib
+    import shutil
+    import subprocess
+    root = pathlib.Path(__file__).resolve().parent.parent
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not pathlib.Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    libdir = pkg._lib.lib_path().parent
+    exe = tmp_path / "c_abi_demo"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-I", str(root / "include"),
+                    str(root / "examples" / "c_abi_demo.cu"), "-L", str(libdir), "-lb2lddmm",
+                    "-Xlinker", f"-rpath={libdir}", "-o", str(exe)], check=True, capture_output=True)
+    dump = tmp_path / "out.bin"
+    r = subprocess.run([str(exe), str(dump)], check=True, capture_output=True, text=True)
+    assert "sum_abs_u" in r.stdout
+    B, T1, H, W, S = 2, 3, 64, 64, 4
+    N, P = H * W, B * T1
+    raw = np.fromfile(dump, dtype=np.float32)
+    sizes = [P * 2 * N, B * (T1 + 1) * N, P * 2 * N, P * N, B * 126 * 40]
+    v0, vol, u, sdef, Sm = [torch.from_numpy(a.copy()) for a in np.split(raw, np.cumsum(sizes)[:-1])]
+    vold = vol.view(B, 1, T1 + 1, H, W).to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vold, "Lagrangian", 3)
+    out = pkg.shoot_warp_strain(v0.view(P, 2, H, W).to(dev), sv, tv, pkg.FluidMetric(PARAMS), num_steps=S)
+    assert torch.equal(out["displacement"].cpu().view(-1), u)
+    assert torch.equal(out["deformed_source"].cpu().view(-1), sdef)
+    assert torch.equal(out["strain_matrix"].cpu().view(-1), Sm)
+
+
+def test_stream_ordered_and_graph_capturable(pkg, dev):
+    """C-ABI contract: every call is ordered on the caller's stream and neither allocates nor synchronises, so a
+    whole forward (fused kernel) and an op-level chain can be captured in a CUDA graph and replayed."""
+    B, T, H, W, S = 2, 3, 64, 64, 3
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 36, 2.0).to(dev)
+    metric = pkg.FluidMetric(PARAMS)
+    eager = pkg.shoot_warp_strain(v0, sv, tv, metric, num_steps=S)
+    eager_ops = pkg.compose_disp_vel(pkg.Ad_star(eager["displacement"], eager["momentum"]),
+                                     metric.sharp(eager["momentum"]), -0.1)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side), torch.no_grad():
+        pkg.shoot_warp_strain(v0, sv, tv, metric, num_steps=S)       # warm-up on the side stream (allocator, tables)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            cap = pkg.shoot_warp_strain(v0, sv, tv, metric, num_steps=S)
+            cap_ops = pkg.compose_disp_vel(pkg.Ad_star(cap["displacement"], cap["momentum"]),
+                                           metric.sharp(cap["momentum"]), -0.1)
+        for _ in range(2):
+            graph.replay()
+    side.synchronize()
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
+        assert torch.equal(cap[k], eager[k]), k
+    assert torch.equal(cap_ops, eager_ops)
