@@ -16,34 +16,33 @@ from .strain import N_SECTORS, strain_matrix
 
 
 def split_vol_to_registration_pairs(vol, split_method: str = "Lagrangian", output_dim: int = 3):
-    """/root/reference/modules/data/__init__.py:93-121."""
-    B, C, T, H, W = vol.shape
-    assert T > 1, f"n_frames should be larger than 1, but got {T}"
+    """Pair construction, behaviour of /root/reference/modules/data/__init__.py:93-121 (golden-checked)."""
+    n_slices, n_chan, n_t, hh, ww = vol.shape
+    assert n_t > 1, f"n_frames should be larger than 1, but got {n_t}"
+    t_idx = torch.arange(1, n_t)
     if split_method == "Lagrangian":
-        src = vol[:, :, :1].repeat(1, 1, T - 1, 1, 1)
-        tar = vol[:, :, 1:]
+        s_idx = torch.zeros(n_t - 1, dtype=torch.long)
     elif split_method == "Eulerian":
-        src = vol[:, :, :-1]
-        tar = vol[:, :, 1:]
+        s_idx = t_idx - 1
     else:
         raise ValueError(f"Unrecognized split_method: {split_method}")
+    src, tar = vol.index_select(2, s_idx), vol.index_select(2, t_idx)
     if output_dim == 2:
-        src = src.reshape(B * (T - 1), C, H, W)
-        tar = tar.reshape(B * (T - 1), C, H, W)
+        src = src.reshape(-1, n_chan, hh, ww)
+        tar = tar.reshape(-1, n_chan, hh, ww)
     return src, tar
 
 
 def align_n_frames_to(volume: np.ndarray, n_target_frames: int, frame_idx: int = -1,
                       padding_method: str = "edge"):
-    """/root/reference/modules/data/datareader/DENSE_IO_utils.py:2-46."""
-    n = volume.shape[frame_idx]
+    """Frame alignment, behaviour of /root/reference/modules/data/datareader/DENSE_IO_utils.py:2-46 (golden-checked)."""
+    moved = np.moveaxis(volume, frame_idx, -1)
+    n = moved.shape[-1]
     if n >= n_target_frames:
-        sl = [slice(None)] * volume.ndim
-        sl[frame_idx] = slice(0, n_target_frames)
-        return volume[tuple(sl)]
-    pads = [(0, 0)] * volume.ndim
-    pads[frame_idx] = (0, n_target_frames - n)
-    return np.pad(volume, pads, mode=padding_method)
+        out = moved[..., :n_target_frames]
+    else:
+        out = np.pad(moved, [(0, 0)] * (moved.ndim - 1) + [(0, n_target_frames - n)], mode=padding_method)
+    return np.moveaxis(out, -1, frame_idx)
 
 
 def forward_pairs(v0, src, tar, metric: FluidMetric, num_steps: int = 10,
