@@ -232,12 +232,27 @@ shoot_fwd_kernel(const ShootParams prm) {
   }
 }
 
+// Resident CTAs per SM of the fused kernel as the runtime reports it (shared memory, registers and threads all
+// count): the persistent grid is #SMs x this, and the per-CTA scratch is sized from the same number.
 template <int H, int W, int NT>
 struct FusedCfg {
   static int ctas_per_sm() {
-    int per = (int)((224 * 1024) / (ShootSmem<H, W>::bytes + 1024));
-    if (per < 1) per = 1;
-    if (per * NT > 2048) per = 2048 / NT;
+    static int cached = 0;
+    if (cached) return cached;
+    const size_t smem = ShootSmem<H, W>::bytes;
+    int per = 0;
+    if (cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP>, NT, smem) !=
+            cudaSuccess ||
+        per < 1) {
+      (void)cudaGetLastError();   // no device / query failed: fall back to the shared-memory bound
+      per = (int)((224 * 1024) / (smem + 1024));
+      if (per < 1) per = 1;
+      if (per * NT > 2048) per = 2048 / NT;
+      return per;                 // not cached: a later call with a device may do better
+    }
+    cached = per;
     return per;
   }
 };
@@ -267,7 +282,7 @@ static int64_t fused_grid(int64_t P, int64_t H) {
     case 16: per = FusedCfg<16, 16, 128>::ctas_per_sm(); break;
     case 32: per = FusedCfg<32, 32, 256>::ctas_per_sm(); break;
     case 64: per = FusedCfg<64, 64, 256>::ctas_per_sm(); break;
-    case 128: per = 1; break;
+    case 128: per = nt128() == 1024 ? FusedCfg<128, 128, 1024>::ctas_per_sm() : FusedCfg<128, 128, 512>::ctas_per_sm(); break;
   }
   int64_t g = (int64_t)sm_count() * per;
   return g < P ? g : P;
