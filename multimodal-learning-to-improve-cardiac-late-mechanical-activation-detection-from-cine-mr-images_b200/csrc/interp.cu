@@ -9,7 +9,10 @@
 
 namespace b2 {
 
-constexpr int kThreads = 256;
+#ifndef B2_OP_THREADS
+#define B2_OP_THREADS 128
+#endif
+constexpr int kThreads = B2_OP_THREADS;
 #ifndef B2_PAIRS_PER_THREAD
 #define B2_PAIRS_PER_THREAD 1
 #endif
