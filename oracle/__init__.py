@@ -15,6 +15,10 @@ Appendix A) and is pinned only by (i) the invariants of SURVEY.md section 8c and
 (ii) the in-tree pieces that *are* importable: ``modules.loss`` (loss boundary),
 ``split_vol_to_registration_pairs`` and ``align_n_frames_to`` - see
 ``tests/golden/make_golden.py``.
+
+Two independent restatements live here and cross-check each other: this torch package (differentiable, any
+dtype) and ``lddmm_c.c`` (plain C, own FFT, OpenMP; wrapped by ``oracle.c_oracle``), which is also the
+multi-threaded CPU baseline of ``bench.py``.
 """
 from .lddmm import (  # noqa: F401
     Conventions,

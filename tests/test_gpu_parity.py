@@ -291,6 +291,21 @@ def test_eulerian_split(pkg, oracle, dev, hw, materialise):
     assert all(torch.equal(a[k], b[k]) for k in a)
 
 
+def test_forward_volume_vs_c_oracle(pkg, dev):
+    """CUDA path against the second, independently written oracle (plain C, own FFT) at the BASELINE grid size."""
+    from oracle import c_oracle
+    B, T, H, W, S = 2, 4, 128, 128, 10
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 37, 3.0)
+    ref = c_oracle.forward_volume(v0, vol, PARAMS, S)
+    vd = vol.to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vd, "Lagrangian", 3)
+    out = pkg.shoot_warp_strain(v0.to(dev), sv, tv, pkg.FluidMetric(PARAMS), num_steps=S)
+    for k in ("momentum", "velocity", "displacement", "strain_matrix"):
+        assert relerr(out[k], ref[k]) < TOL, f"{k}: {relerr(out[k], ref[k]):.2e}"
+    assert relerr(out["deformed_source"], ref["deformed_source"]) < 3e-5      # binary mask: |du| in pixels
+
+
 def test_forward_volume_backward(pkg, oracle, dev):
     """Training-mode gradients through shooting + warp + strain vs autograd through the oracle."""
     B, T, H, W, S = 2, 4, 32, 32, 4

@@ -260,3 +260,22 @@ def test_forward_volume_contract(oracle):
     assert out["velocity"].shape == out["momentum"].shape == (B * (T - 1), 2, H, W)
     loss = oracle.registration_reconstruction_loss(out, {"registration_target": tar_vol})
     assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("cfg", [(2, 3, 32, 32, 3), (1, 4, 64, 64, 6), (1, 3, 32, 64, 2)])
+def test_c_oracle_matches_torch(oracle, pkg, cfg):
+    """The two independently written oracles (plain C with its own FFT / torch) agree on every output."""
+    from oracle import c_oracle
+    B, T, H, W, S = cfg
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    v0 = pkg.synthetic.synthetic_v0(B * (T - 1), H, W, seed=41, max_disp=3.0)
+    sv, tv = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    ref = oracle.forward_volume(v0, sv, tv, oracle.FluidMetric((1.0, 0.1, 0.05)), S)
+    out = c_oracle.forward_volume(v0, vol, (1.0, 0.1, 0.05), S, nthreads=2)
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
+        assert out[k].shape == ref[k].shape
+        assert relerr(out[k], ref[k]) < 1e-5, f"{k}: {relerr(out[k], ref[k]):.2e}"
+    import ctypes
+    tab = (ctypes.c_int32 * 252)()
+    c_oracle.lib().b2o_sector_table(126, tab)
+    assert np.array_equal(np.array(list(tab)).reshape(126, 2), oracle.sector_boundaries(126))
