@@ -77,7 +77,7 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
         ws = _workspace(nbytes, dev)
     check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), nbytes, stream()), "b2_shoot_fwd")
     fused = (H == W and H in (16, 32, 64, 128))
-    _lib.count_launch(1 if fused else 3 + 5 * int(num_steps) + 2)
+    _lib.count_launch(1 if fused else 3 + 3 * int(num_steps) + 2)   # path B: flat, 3 kernels per step, warp, strain
     return out
 
 

@@ -132,6 +132,15 @@ def test_errors_on_gpu(pkg, dev):
         pkg.interp(torch.zeros(1, 1, 8, 8, device=dev, dtype=torch.float64), torch.zeros(1, 2, 8, 8, device=dev))
     with pytest.raises(RuntimeError):
         pkg.FluidMetric(PARAMS).sharp(torch.zeros(1, 2, 48, 48, device=dev))   # not a supported FFT size
+    vol = torch.zeros(2, 1, 3, 32, 32, device=dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    with pytest.raises(RuntimeError):                                          # v0 batch does not match B*(T-1)
+        pkg.shoot_warp_strain(torch.zeros(3, 2, 32, 32, device=dev), sv, tv, pkg.FluidMetric(PARAMS))
+    with pytest.raises(RuntimeError):                                          # 48x48: no FFT path
+        pkg.shoot_warp_strain(torch.zeros(4, 2, 48, 48, device=dev), torch.zeros(2, 1, 2, 48, 48, device=dev),
+                              torch.zeros(2, 1, 2, 48, 48, device=dev), pkg.FluidMetric(PARAMS))
+    with pytest.raises(RuntimeError):                                          # more sectors than the fused kernel bins
+        pkg.shoot_warp_strain(torch.zeros(4, 2, 32, 32, device=dev), sv, tv, pkg.FluidMetric(PARAMS), n_sectors=512)
 
 
 @pytest.mark.parametrize("disp,tr", [(True, False), (True, True), (False, False), (False, True)])
