@@ -249,6 +249,26 @@ def test_strain_matrix(pkg, oracle, dev, n_frames):
               lambda a: oracle.strain_matrix(a, tar, mask0, n_frames=n_frames), [u])
 
 
+def test_strain_analytic_on_gpu(pkg, dev):
+    """Known answers on the GPU kernel itself: a rigid inverse map gives zero strain, a uniform radial scaling s
+    gives Ecc = (s^2 - 1)/2 in all 126 sectors (SURVEY.md 8c invariants)."""
+    import math
+    H = W = 64
+    rr = torch.arange(H, dtype=torch.float32).view(H, 1).expand(H, W) - (H - 1) / 2
+    cc = torch.arange(W, dtype=torch.float32).view(1, W).expand(H, W) - (W - 1) / 2
+    rad = torch.sqrt(rr * rr + cc * cc)
+    m = ((rad >= 10) & (rad <= 29)).float()
+    mask0, tar = m.expand(1, H, W).contiguous(), m.expand(1, 2, H, W).contiguous()
+    th, s = 0.2, 1.1
+    u_rot = torch.stack([math.cos(th) * rr - math.sin(th) * cc - rr + 1.5, math.sin(th) * rr + math.cos(th) * cc - cc - 0.5])
+    u_sc = torch.stack([rr / s - rr, cc / s - cc])
+    u = torch.stack([u_rot, u_sc]).unsqueeze(0)
+    S, cnt = pkg.strain_matrix(u.to(dev), tar.to(dev), mask0.to(dev), n_frames=None, return_counts=True)
+    assert (cnt > 0).all()
+    assert S[0, 0, :, 0].abs().max() < 2e-6
+    assert (S[0, 0, :, 1] - (s * s - 1) / 2).abs().max() < 2e-6
+
+
 @pytest.mark.parametrize("cfg", [(3, 3, 16, 16, 3), (2, 4, 32, 32, 3), (2, 5, 64, 64, 10), (1, 3, 128, 128, 10),
                                  (1, 3, 256, 256, 2), (2, 3, 64, 128, 3), (1, 3, 128, 256, 2)])
 def test_forward_volume_parity(pkg, oracle, dev, cfg):
