@@ -302,6 +302,200 @@ static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
   return B2_OK;
 }
 
+// ------------------------------------------------------------------ fused EPDiff adjoint (path A)
+// Reverse sweep over the saved trajectory, one CTA per frame-pair at a time, same residency scheme as the
+// forward: dL/dv_s -> dL/dm_s lives in shared memory (the self-adjoint sharp is the in-SM FFT), the gradient
+// accumulators dL/du (ping-pong), dL/dm0 and w = m0 o (id + u_s) sit in per-CTA global scratch that stays in L2.
+// Buffers that receive float atomics (RED goes to L2) are only ever READ with ld.global.cg, so a stale L1 line
+// can never be observed; u_s, v_s and m0 are read-only for this kernel (ld.global.nc).
+struct ShootBwdParams {
+  const float* gu;      // dL/du^S   (P,2,H,W) or nullptr
+  const float* gvel;    // dL/dvel   or nullptr
+  const float* gm0;     // explicit dL/dm0 or nullptr
+  const float* m0;
+  const float* traj;    // (S, 2, P, 2, H, W)
+  float* gv0;
+  float* scratch;       // per CTA: [G ping | G pong | dL/dm0 | w]
+  int64_t P, field;
+  int num_steps, v0_is_momentum;
+  float alpha, beta, gamma, T;
+};
+
+template <int H, int W, int NT, int BG>
+__global__ void __launch_bounds__(NT)
+shoot_bwd_kernel(const ShootBwdParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using FS = FluidSmem<H, W>;
+  static_assert(NT % W == 0 && H % (NT / W) == 0, "CTA must tile the grid in whole row bands");
+  constexpr int LD = FS::LD, N = H * W, RB = NT / W, NB = H / RB;
+  float2 *z, *twH, *twW, *csH, *csW;
+  FS::carve(smem_raw, z, twH, twW, csH, csW);
+  const int tid = threadIdx.x;
+  const int c = tid % W, br = tid / W;
+  const int S = prm.num_steps;
+  const float mdt = -prm.T / (float)S;
+  const FluidParams fp{prm.alpha, prm.beta, prm.gamma, 1.0f / (float)N};
+  const int64_t P = prm.P;
+  const int cl = max(c - 1, 0), cr = min(c + 1, W - 1);
+  const float sc = diff_scale(c, W);
+  const float cmc = (c >= 1) ? diff_scale(c - 1, W) : 0.f, cpc = (c <= W - 2) ? diff_scale(c + 1, W) : 0.f;
+  const float c0c = (c == W - 1 ? 1.f : 0.f) - (c == 0 ? 1.f : 0.f);
+  FS::init_luts(twH, twW, csH, csW, tid, NT);
+  float* Ga = prm.scratch + (size_t)blockIdx.x * 4 * prm.field;
+  float* Gb = Ga + prm.field;
+  float* A = Gb + prm.field;
+  float* Wb = A + prm.field;
+  __syncthreads();
+
+  for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
+    const float* m0p = prm.m0 + (size_t)p * prm.field;
+    float* Gcur = Ga;
+    float* Gnext = Gb;
+    for (int k = 0; k < NB; ++k) {
+      const int i = (k * RB + br) * W + c;
+      Gcur[i] = prm.gu ? __ldg(prm.gu + (size_t)p * prm.field + i) : 0.f;
+      Gcur[N + i] = prm.gu ? __ldg(prm.gu + (size_t)p * prm.field + N + i) : 0.f;
+      A[i] = prm.gm0 ? __ldg(prm.gm0 + (size_t)p * prm.field + i) : 0.f;
+      A[N + i] = prm.gm0 ? __ldg(prm.gm0 + (size_t)p * prm.field + N + i) : 0.f;
+    }
+    __syncthreads();
+
+    for (int s = S - 1; s >= 0; --s) {
+      const float* us = prm.traj + ((size_t)(2 * s) * P + p) * prm.field;
+      const float* vs = prm.traj + ((size_t)(2 * s + 1) * P + p) * prm.field;
+      if (s > 0) {
+        // ---- adjoint of u_{s+1} = interp(u_s, v_s, -dt) - dt v_s : dL/dv_s -> z, splat of dL/du_{s+1} -> Gnext
+        for (int k = 0; k < NB; ++k) {
+          const int i = (k * RB + br) * W + c;
+          Gnext[i] = 0.f;
+          Gnext[N + i] = 0.f;
+        }
+        __syncthreads();
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          const float g0 = __ldcg(Gcur + i), g1 = __ldcg(Gcur + N + i);
+          const float v0 = __ldg(vs + i), v1 = __ldg(vs + N + i);
+          const Taps t = make_taps<BG>((float)r + mdt * v0, (float)c + mdt * v1, H, W);
+          float a0, a1, b0, b1;
+          tap_grad<BG>(t, __ldg(us + t.o00), __ldg(us + t.o10), __ldg(us + t.o01), __ldg(us + t.o11), a0, a1);
+          tap_grad<BG>(t, __ldg(us + N + t.o00), __ldg(us + N + t.o10), __ldg(us + N + t.o01), __ldg(us + N + t.o11), b0, b1);
+          z[r * LD + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
+          const float oma = 1.f - t.a, omb = 1.f - t.b;
+          float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
+          if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
+          atomicAdd(Gnext + t.o00, w00 * g0); atomicAdd(Gnext + t.o01, w01 * g0);
+          atomicAdd(Gnext + t.o10, w10 * g0); atomicAdd(Gnext + t.o11, w11 * g0);
+          atomicAdd(Gnext + N + t.o00, w00 * g1); atomicAdd(Gnext + N + t.o01, w01 * g1);
+          atomicAdd(Gnext + N + t.o10, w10 * g1); atomicAdd(Gnext + N + t.o11, w11 * g1);
+        }
+      } else {
+        // u_0 = 0: u_1 = -dt v_0, so dL/dv_0 = -dt dL/du_1 (+ the direct gradient of the velocity output)
+        const float* gv = prm.gvel ? prm.gvel + (size_t)p * prm.field : nullptr;
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          float a = mdt * __ldcg(Gcur + i), b = mdt * __ldcg(Gcur + N + i);
+          if (gv) { a += __ldg(gv + i); b += __ldg(gv + N + i); }
+          z[r * LD + c] = make_float2(a, b);
+        }
+      }
+      __syncthreads();
+      // ---- dL/dm_s = sharp(dL/dv_s)   (self-adjoint)
+      fluid_smem<H, W, true, NT>(z, twH, twW, csH, csW, fp, tid);
+      if (s > 0) {
+        // ---- adjoint of m_s = (I + Du_s)^T (m0 o (id + u_s)); first w = m0 o (id + u_s) for the stencils
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
+          Wb[i] = tap_sample<BG>(t, __ldg(m0p + t.o00), __ldg(m0p + t.o10), __ldg(m0p + t.o01), __ldg(m0p + t.o11));
+          Wb[N + i] = tap_sample<BG>(t, __ldg(m0p + N + t.o00), __ldg(m0p + N + t.o10), __ldg(m0p + N + t.o01),
+                                     __ldg(m0p + N + t.o11));
+        }
+        __syncthreads();
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
+          const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
+          const float sr = diff_scale(r, H);
+          const float d00 = sr * (__ldg(us + odn) - __ldg(us + oup)), d10 = sr * (__ldg(us + N + odn) - __ldg(us + N + oup));
+          const float d01 = sc * (__ldg(us + ort) - __ldg(us + olf)), d11 = sc * (__ldg(us + N + ort) - __ldg(us + N + olf));
+          const float2 g = z[r * LD + c];
+          const float gw0 = g.x + (d00 * g.x + d01 * g.y);
+          const float gw1 = g.y + (d10 * g.x + d11 * g.y);
+          const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
+          const float oma = 1.f - t.a, omb = 1.f - t.b;
+          float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
+          if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
+          atomicAdd(A + t.o00, w00 * gw0); atomicAdd(A + t.o01, w01 * gw0);
+          atomicAdd(A + t.o10, w10 * gw0); atomicAdd(A + t.o11, w11 * gw0);
+          atomicAdd(A + N + t.o00, w00 * gw1); atomicAdd(A + N + t.o01, w01 * gw1);
+          atomicAdd(A + N + t.o10, w10 * gw1); atomicAdd(A + N + t.o11, w11 * gw1);
+          float a0, a1, b0, b1;
+          tap_grad<BG>(t, __ldg(m0p + t.o00), __ldg(m0p + t.o10), __ldg(m0p + t.o01), __ldg(m0p + t.o11), a0, a1);
+          tap_grad<BG>(t, __ldg(m0p + N + t.o00), __ldg(m0p + N + t.o10), __ldg(m0p + N + t.o01),
+                       __ldg(m0p + N + t.o11), b0, b1);
+          float o0 = gw0 * a0 + gw1 * b0;
+          float o1 = gw0 * a1 + gw1 * b1;
+          // Jacobian part: du_b += D_0^T (g_0 w_b) + D_1^T (g_1 w_b), gathered form
+          const float cmr = (r >= 1) ? diff_scale(r - 1, H) : 0.f, cpr = (r <= H - 2) ? diff_scale(r + 1, H) : 0.f;
+          const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
+          const float gu_ = z[ru * LD + c].x, gd_ = z[rd * LD + c].x, gl_ = z[r * LD + cl].y, gr_ = z[r * LD + cr].y;
+          const float w0c = Wb[i], w1c = Wb[N + i];
+          o0 += (cmr * (gu_ * Wb[oup]) + c0r * (g.x * w0c) - cpr * (gd_ * Wb[odn]))
+              + (cmc * (gl_ * Wb[olf]) + c0c * (g.y * w0c) - cpc * (gr_ * Wb[ort]));
+          o1 += (cmr * (gu_ * Wb[N + oup]) + c0r * (g.x * w1c) - cpr * (gd_ * Wb[N + odn]))
+              + (cmc * (gl_ * Wb[N + olf]) + c0c * (g.y * w1c) - cpc * (gr_ * Wb[N + ort]));
+          atomicAdd(Gnext + i, o0);       // own pixel; atomics keep every access to G on the L2 path
+          atomicAdd(Gnext + N + i, o1);
+        }
+        float* tmp = Gcur; Gcur = Gnext; Gnext = tmp;
+      } else {
+        // m_0 = Ad*_0 m0 = m0 exactly
+        for (int k = 0; k < NB; ++k) {
+          const int r = k * RB + br, i = r * W + c;
+          const float2 g = z[r * LD + c];
+          atomicAdd(A + i, g.x);
+          atomicAdd(A + N + i, g.y);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- dL/dv0 = flat(dL/dm0)  (or dL/dm0 itself when the forward input was the momentum)
+    for (int k = 0; k < NB; ++k) {
+      const int r = k * RB + br, i = r * W + c;
+      z[r * LD + c] = make_float2(__ldcg(A + i), __ldcg(A + N + i));
+    }
+    __syncthreads();
+    if (!prm.v0_is_momentum) fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
+    float* out = prm.gv0 + (size_t)p * prm.field;
+    for (int k = 0; k < NB; ++k) {
+      const int r = k * RB + br, i = r * W + c;
+      const float2 v = z[r * LD + c];
+      out[i] = v.x;
+      out[N + i] = v.y;
+    }
+    __syncthreads();
+  }
+}
+
+template <int H, int W, int NT>
+static int launch_fused_bwd(const ShootBwdParams& prm, int background, cudaStream_t st) {
+  const size_t smem = FluidSmem<H, W>::bytes;
+  int per = (int)((224 * 1024) / (smem + 1024));
+  if (per < 1) per = 1;
+  if (per * NT > 2048) per = 2048 / NT;
+  int64_t grid = (int64_t)sm_count() * per;
+  if (grid > prm.P) grid = prm.P;
+  if (background == B2_BG_CLAMP) {
+    B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP><<<(unsigned)grid, NT, smem, st>>>(prm);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shoot_bwd_kernel<H, W, NT, B2_BG_ZERO><<<(unsigned)grid, NT, smem, st>>>(prm);
+  }
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
 // ------------------------------------------------------------------ small elementwise helpers
 __global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -429,6 +623,17 @@ extern "C" int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0
   if (num_steps < 1 || !(gamma > 0.f) || !(T > 0.f)) return B2_E_PARAM;
   if (!workspace || workspace_bytes < b2_shoot_bwd_workspace_bytes(P, H, W)) return B2_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  if (fused_size(H, W) && !getenv("B2_BWD_OPLEVEL")) {
+    // path A: one persistent kernel; scratch = (resident CTAs) x 4 fields <= 5 P fields of the op-level layout
+    ShootBwdParams prm{gu, gvel, gm0, m0, traj, gv0, reinterpret_cast<float*>(workspace), P, 2 * H * W,
+                       num_steps, v0_is_momentum, alpha, beta, gamma, T};
+    switch ((int)H) {
+      case 16: return launch_fused_bwd<16, 16, 128>(prm, background, st);
+      case 32: return launch_fused_bwd<32, 32, 256>(prm, background, st);
+      case 64: return launch_fused_bwd<64, 64, 256>(prm, background, st);
+      case 128: return launch_fused_bwd<128, 128, 1024>(prm, background, st);
+    }
+  }
   const size_t n = (size_t)P * 2 * H * W, fbytes = align256(sizeof(float) * n);
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   float* g_u = reinterpret_cast<float*>(ws);                  // dL/du_{s+1}
