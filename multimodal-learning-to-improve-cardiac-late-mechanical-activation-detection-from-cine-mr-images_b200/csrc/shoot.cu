@@ -302,6 +302,17 @@ static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
   return B2_OK;
 }
 
+#ifndef B2_BWD_U1
+#define B2_BWD_U1 4
+#endif
+#ifndef B2_BWD_U3A
+#define B2_BWD_U3A 4
+#endif
+#ifndef B2_BWD_U3B
+#define B2_BWD_U3B 2
+#endif
+constexpr int kBwdUnrollB1 = B2_BWD_U1, kBwdUnrollB3a = B2_BWD_U3A, kBwdUnrollB3b = B2_BWD_U3B;
+
 // ------------------------------------------------------------------ fused EPDiff adjoint (path A)
 // Reverse sweep over the saved trajectory, one CTA per frame-pair at a time, same residency scheme as the
 // forward: dL/dv_s -> dL/dm_s lives in shared memory (the self-adjoint sharp is the in-SM FFT), the gradient
@@ -371,6 +382,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           Gnext[N + i] = 0.f;
         }
         __syncthreads();
+#pragma unroll (kBwdUnrollB1)
         for (int k = 0; k < NB; ++k) {
           const int r = k * RB + br, i = r * W + c;
           const float g0 = __ldcg(Gcur + i), g1 = __ldcg(Gcur + N + i);
@@ -403,6 +415,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       fluid_smem<H, W, true, NT>(z, twH, twW, csH, csW, fp, tid);
       if (s > 0) {
         // ---- adjoint of m_s = (I + Du_s)^T (m0 o (id + u_s)); first w = m0 o (id + u_s) for the stencils
+#pragma unroll (kBwdUnrollB3a)
         for (int k = 0; k < NB; ++k) {
           const int r = k * RB + br, i = r * W + c;
           const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
@@ -411,6 +424,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
                                      __ldg(m0p + N + t.o11));
         }
         __syncthreads();
+#pragma unroll (kBwdUnrollB3b)
         for (int k = 0; k < NB; ++k) {
           const int r = k * RB + br, i = r * W + c;
           const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
