@@ -29,6 +29,12 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
                     int64_t P, int64_t H, int64_t W, int background, bool zero_dm0, cudaStream_t st,
                     const float* du_add);
 
+// 256x256: one 4-CTA cluster per pair (shoot_cluster.cu)
+int cluster_grid_clusters(int64_t P);
+int64_t cluster_workspace_bytes(int64_t P);
+int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t st);
+static bool cluster_size(int64_t H, int64_t W) { return H == 256 && W == 256 && !getenv("B2_NO_CLUSTER"); }
+
 int epdiff_step_big(const float* u, const float* m0, float* unext, float* vout, void* zg, int64_t P, int64_t H,
                     int64_t W, float alpha, float beta, float gamma, float dt, int bg, cudaStream_t st);
 
@@ -533,6 +539,7 @@ extern "C" int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, in
   if (B <= 0 || T1 <= 0 || H <= 0 || W <= 0 || num_steps <= 0) return 0;
   const int64_t P = B * T1, field = 2 * H * W;
   if (fused_size(H, W)) return (int64_t)align256(sizeof(float) * (size_t)fused_grid(P, H) * 2 * field);
+  if (cluster_size(H, W)) return (int64_t)align256((size_t)cluster_workspace_bytes(P));
   // path B: m0 (if not given) + u scratch + m/v buffer + FFT scratch
   return (int64_t)(3 * align256(sizeof(float) * (size_t)P * field) + align256((size_t)b2_fluid_workspace_bytes(P, H, W)));
 }
@@ -569,6 +576,11 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
                                        : launch_fused<128, 128, 512>(prm, grid, st);
     }
     return B2_E_FFTSIZE;
+  }
+
+  if (cluster_size(H, W)) {
+    if (a.S && (a.n_sectors > kMaxSectors)) return B2_E_PARAM;
+    return launch_shoot_cluster(a, workspace, st);
   }
 
   // ---- path B: op-level sequence

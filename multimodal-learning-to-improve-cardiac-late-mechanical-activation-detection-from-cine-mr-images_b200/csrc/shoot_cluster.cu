@@ -1,0 +1,328 @@
+// Fused geodesic shooting for 256x256 grids: one 4-CTA thread-block cluster per frame-pair.
+//
+// A 256x256 complex field is 512 KiB - it does not fit one SM - so the pair is split into four 64-row slabs, one per
+// CTA of a cluster (4 SMs).  Row FFTs run on the slab in shared memory; for the column pass the four CTAs exchange
+// data through a per-pair scratch that stays in L2: every CTA stores its slab, the cluster synchronises, and every
+// CTA loads a MIRROR-CLOSED group of 64 spectrum columns (4 blocks of 16 cells: {0,8,1,15}, {2,14,3,13}, ...), so
+// the k <-> -k coupling of the fluid multiplier stays inside one CTA.  m / v never reach HBM; u_s and m0 live in the
+// same per-pair L2 scratch (2.5 MiB per cluster, ~92 MiB for 37 clusters) and are re-read by the gathers.
+// Three cluster barriers per EPDiff step (after compose, after the row pass, after the column pass).
+#include <cooperative_groups.h>
+
+#include "fft.cuh"
+#include "strain.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace b2 {
+
+constexpr int kCH = 256, kCW = 256, kCL = 4, kCNT = 1024, kSR = kCH / kCL;   // slab rows per CTA
+constexpr int kLDR = kCW + 1;      // row-slab pitch   (64 rows x 257)
+constexpr int kLDC = kSR + 1;      // column-slab pitch (256 rows x 65)
+constexpr int kCN = kCH * kCW;
+
+__constant__ int c_group_block[4][4] = {{0, 8, 1, 15}, {2, 14, 3, 13}, {4, 12, 5, 11}, {6, 10, 7, 9}};
+
+struct ClusterParams {
+  b2_shoot_args a;
+  float* scratch;        // per cluster: [Zs (complex, 2 fields) | u ping | u pong | m0] + bins
+  int64_t P;
+  int64_t cluster_stride;   // floats of scratch per cluster
+};
+
+__device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? (q < 2 ? q : 5 - q) : (q ^ 1); }
+
+template <int BG>
+__global__ void __launch_bounds__(kCNT)
+shoot_cluster_kernel(const ClusterParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rk = (int)cluster.block_rank();            // slab index == column-group index
+  const int64_t ncl = gridDim.x / kCL;
+  constexpr int H = kCH, W = kCW, N = kCN;
+  float2* z = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = z + (size_t)H * kLDC;                   // 256 x 65 >= 64 x 257
+  float2* cs = tw + 256;
+  const b2_shoot_args& a = prm.a;
+  const int tid = threadIdx.x;
+  const int S = a.num_steps;
+  const float mdt = -a.T / (float)S;
+  const FluidParams fp{a.alpha, a.beta, a.gamma, 1.0f / (float)N};
+  init_twiddles<256>(tw, tid, kCNT);
+  init_symbol_lut<256>(cs, tid, kCNT);
+  // pixel phases: a thread keeps one column and walks 16 rows of the slab
+  const int c = tid % W, br = tid / W;                 // br in [0,4)
+  constexpr int RBc = kCNT / W, NBc = kSR / RBc;       // 4 rows per band, 16 bands
+  const int r0 = rk * kSR;
+  // column phases: a thread keeps one local column of the group
+  const int lc = tid % kSR, q = lc / 16, cc = lc % 16;
+  const int pc = c_group_block[rk][q] * 16 + cc;        // global spectrum cell column
+  __syncthreads();
+
+  for (int64_t p = blockIdx.x / kCL; p < prm.P; p += ncl) {
+    float* base = prm.scratch + (size_t)(blockIdx.x / kCL) * prm.cluster_stride;
+    float2* Zs = reinterpret_cast<float2*>(base);
+    float* ubuf0 = base + 2 * (size_t)N;
+    float* ubuf1 = ubuf0 + 2 * (size_t)N;
+    float* m0s = ubuf1 + 2 * (size_t)N;
+    unsigned long long* bins = reinterpret_cast<unsigned long long*>(m0s + 2 * (size_t)N);   // sums[n], then counts
+    const int64_t b = p / a.T1;
+    const int t = (int)(p % a.T1);
+    const float* v0p = a.v0 + (size_t)p * 2 * N;
+    float* m0g = (a.m0 && !a.v0_is_momentum) ? a.m0 + (size_t)p * 2 * N : m0s;
+    const float* m0r = a.v0_is_momentum ? v0p : m0g;
+    float* uout = a.u + (size_t)p * 2 * N;
+
+    // one fluid operator on the slab in z (row layout in, row layout out)
+    auto fluid = [&](bool inverse) {
+      fft_lines<256, kSR, -1, kCNT, 1, kLDR>(z, tw, tid);
+      for (int k = 0; k < NBc; ++k) {                   // slab -> L2 scratch (cell order along c)
+        const int lr = k * RBc + br;
+        Zs[(size_t)(r0 + lr) * W + c] = z[lr * kLDR + c];
+      }
+      __threadfence();
+      cluster.sync();
+      for (int i = tid; i < H * kSR; i += kCNT) {       // mirror-closed column group, all 256 rows
+        const int r = i / kSR;
+        z[r * kLDC + lc] = Zs[(size_t)r * W + pc];
+      }
+      __syncthreads();
+      fft_lines<256, kSR, -1, kCNT, kLDC, 1>(z, tw, tid);
+      {
+        const int k1 = cell_to_freq<256>(pc);
+        const int qcell = freq_to_cell<256>((W - k1) & (W - 1));
+        const int lc2 = mirror_q(rk, q) * 16 + (qcell & 15);
+        const float2 cs1 = cs[k1];
+        const float h = 0.5f * fp.scale, bs1 = fp.beta * cs1.y;
+        for (int k0 = tid / kSR; k0 <= H / 2; k0 += kCNT / kSR) {
+          const int pr = freq_to_cell<256>(k0), qr = freq_to_cell<256>((H - k0) & (H - 1));
+          if (pr == qr && pc > qcell) continue;
+          const float2 cs0 = cs[k0];
+          const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
+          const float L00 = lam + fp.beta * cs0.x, L11 = lam + fp.beta * cs1.x, L01 = cs0.y * bs1;
+          float A, Br, Bi;
+          if (inverse) {
+            const float idet = __fdividef(h, L00 * L11 - L01 * L01);
+            A = idet * (L11 + L00); Br = idet * (L11 - L00); Bi = -2.0f * idet * L01;
+          } else {
+            A = h * (L00 + L11); Br = h * (L00 - L11); Bi = 2.0f * h * L01;
+          }
+          float2* zp = z + pr * kLDC + lc;
+          float2* zq = z + qr * kLDC + lc2;
+          const float2 Z = *zp, Zq = *zq;
+          *zp = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
+          if (zp != zq) *zq = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
+        }
+        __syncthreads();
+      }
+      fft_lines<256, kSR, +1, kCNT, kLDC, 1>(z, tw, tid);
+      for (int i = tid; i < H * kSR; i += kCNT) {
+        const int r = i / kSR;
+        Zs[(size_t)r * W + pc] = z[r * kLDC + lc];
+      }
+      __threadfence();
+      cluster.sync();
+      for (int k = 0; k < NBc; ++k) {
+        const int lr = k * RBc + br;
+        z[lr * kLDR + c] = Zs[(size_t)(r0 + lr) * W + c];
+      }
+      __syncthreads();
+      fft_lines<256, kSR, +1, kCNT, 1, kLDR>(z, tw, tid);
+    };
+
+    // ---- load v0 (or m0) slab, m0 = flat(v0)
+    for (int k = 0; k < NBc; ++k) {
+      const int lr = k * RBc + br, i = (r0 + lr) * W + c;
+      z[lr * kLDR + c] = make_float2(__ldg(v0p + i), __ldg(v0p + N + i));
+    }
+    __syncthreads();
+    if (!a.v0_is_momentum) {
+      fluid(false);
+      for (int k = 0; k < NBc; ++k) {
+        const int lr = k * RBc + br, i = (r0 + lr) * W + c;
+        const float2 v = z[lr * kLDR + c];
+        m0g[i] = v.x;
+        m0g[N + i] = v.y;
+      }
+      __syncthreads();
+    }
+
+    const float* ucur = nullptr;
+    for (int s = 0; s < S; ++s) {
+      if (s > 0) {
+        // m = Ad*_{u_s} m0 on the slab; u_s and m0 come from the per-pair L2 scratch (neighbour slabs included)
+        const float* u0 = ucur;
+        const float* u1 = ucur + N;
+#pragma unroll 2
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
+          int rlo, rhi, clo, chi; float sr, sc;
+          diff_idx(r, H, rlo, rhi, sr);
+          diff_idx(c, W, clo, chi, sc);
+          const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]), d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+          const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]), d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+          float w0, w1;
+          gather2<BG, false>(m0r, N, (float)r + u0[i], (float)c + u1[i], H, W, w0, w1);
+          z[lr * kLDR + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+        }
+        __syncthreads();
+      }
+      fluid(true);                                     // v = sharp(m), slab in z
+      float* unext = (((S - (s + 1)) & 1) == 0) ? uout : ((s & 1) ? ubuf1 : ubuf0);
+      if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * prm.P + p) * 2 * N : uout;
+      float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * prm.P + p) * 2 * N : nullptr;
+      float* utraj0 = (a.traj && s == 0) ? a.traj + (size_t)p * 2 * N : nullptr;
+      float* velout = (s == 0 && a.vel) ? a.vel + (size_t)p * 2 * N : nullptr;
+#pragma unroll 2
+      for (int k = 0; k < NBc; ++k) {
+        const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
+        const float2 v = z[lr * kLDR + c];
+        float n0 = mdt * v.x, n1 = mdt * v.y;
+        if (s > 0) {
+          float g0, g1;
+          gather2<BG, false>(ucur, N, (float)r + n0, (float)c + n1, H, W, g0, g1);
+          n0 += g0;
+          n1 += g1;
+        }
+        unext[i] = n0;
+        unext[N + i] = n1;
+        if (utraj0) { utraj0[i] = 0.f; utraj0[N + i] = 0.f; }
+        if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
+        if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+      }
+      ucur = unext;
+      __threadfence();
+      cluster.sync();                                  // u_{s+1} of all four slabs visible to the cluster
+    }
+
+    // ---- deformed source on the slab
+    if (a.sdef) {
+      const float* src = a.src_per_pair
+                             ? (a.src_slice_stride ? a.src + (size_t)b * a.src_slice_stride + (size_t)t * N
+                                                   : a.src + (size_t)p * N)
+                             : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
+      float* sd = a.sdef + (size_t)p * N;
+      for (int k = 0; k < NBc; ++k) {
+        const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
+        sd[i] = gather1_ldg<BG>(src, (float)r + ucur[i], (float)c + ucur[N + i], H, W);
+      }
+    }
+    // ---- strain: every CTA bins its slab into the per-pair bins in L2 (integer atomics), rank 0 writes the column
+    if (a.S) {
+      const int ns = a.n_sectors;
+      unsigned int* cnts = reinterpret_cast<unsigned int*>(bins + ns);
+      if (rk == 0)
+        for (int i = tid; i < ns; i += kCNT) { bins[i] = 0ull; cnts[i] = 0u; }
+      __threadfence();
+      cluster.sync();
+      const long long* mom = reinterpret_cast<const long long*>(a.moments) + 3 * b;
+      const long long cnt = mom[0], sx = mom[1], sy = mom[2];
+      float c0, c1;
+      centroid_from_moments(mom, H, W, c0, c1);
+      const float* tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N
+                                             : a.tar + (size_t)p * N;
+      const float* u0 = ucur;
+      const float* u1 = ucur + N;
+      for (int k = 0; k < NBc; ++k) {
+        const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
+        if (!(tarp[i] > 0.5f)) continue;
+        const int ksec = classify_sector(cnt * r - sx, cnt * c - sy, a.table, ns);
+        if (ksec < 0) continue;
+        int rlo, rhi, clo, chi; float sr, sc;
+        diff_idx(r, H, rlo, rhi, sr);
+        diff_idx(c, W, clo, chi, sc);
+        const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]), d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+        const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]), d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+        EccTerms e; float ecc;
+        if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[i], (float)c + u1[i], c0, c1, e, ecc)) continue;
+        atomicAdd(bins + ksec, ecc_to_fixed(ecc));
+        atomicAdd(cnts + ksec, 1u);
+      }
+      __threadfence();
+      cluster.sync();
+      if (rk == 0) {
+        for (int k = tid; k < ns; k += kCNT) {
+          const int cn = (int)__ldcg(cnts + k);
+          const float val = fixed_to_mean(__ldcg(bins + k), cn);
+          float* row = a.S + ((size_t)b * ns + k) * a.n_frames;
+          if (t < a.n_frames) row[t] = val;
+          if (t == (int)a.T1 - 1)
+            for (int tt = (int)a.T1; tt < a.n_frames; ++tt) row[tt] = val;
+          if (a.counts) a.counts[((size_t)b * ns + k) * a.T1 + t] = cn;
+        }
+      }
+    }
+    __threadfence();
+    cluster.sync();                                     // scratch free for the next pair of this cluster
+  }
+}
+
+constexpr size_t kClusterSmem = sizeof(float2) * ((size_t)kCH * kLDC + 512);
+
+static size_t cluster_scratch_floats() { return (size_t)8 * kCN + 4 * kMaxSectors; }   // Zs(2) + u(2x2) + m0(2) fields + bins
+
+template <int BG>
+static int cluster_max_active(int* out) {
+  B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCL * 64);
+  cfg.blockDim = dim3(kCNT);
+  cfg.dynamicSmemBytes = kClusterSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  B2_CUDA(cudaOccupancyMaxActiveClusters(&n, shoot_cluster_kernel<BG>, &cfg));
+  *out = n;
+  return B2_OK;
+}
+
+// number of clusters to launch (co-resident clusters, at most P); 0 when clusters are unavailable
+int cluster_grid_clusters(int64_t P) {
+  static int cached = -1;
+  if (cached < 0) {
+    int n = 0;
+    if (cluster_max_active<B2_BG_CLAMP>(&n) != B2_OK || n < 1) { (void)cudaGetLastError(); return 0; }
+    cached = n;
+  }
+  return (int)(cached < P ? cached : P);
+}
+
+int64_t cluster_workspace_bytes(int64_t P) {
+  int n = cluster_grid_clusters(P);
+  if (n < 1) n = 37 < P ? 37 : (int)P;                 // no device (size query on a CPU box): assume a full B200
+  return (int64_t)(sizeof(float) * cluster_scratch_floats() * (size_t)n);
+}
+
+int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t st) {
+  const int64_t P = a.B * a.T1;
+  const int ncl = cluster_grid_clusters(P);
+  if (ncl < 1) return B2_E_FFTSIZE;
+  ClusterParams prm;
+  prm.a = a;
+  prm.scratch = reinterpret_cast<float*>(workspace);
+  prm.P = P;
+  prm.cluster_stride = (int64_t)cluster_scratch_floats();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(kCL * ncl));
+  cfg.blockDim = dim3(kCNT);
+  cfg.dynamicSmemBytes = kClusterSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (a.background == B2_BG_CLAMP) {
+    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_kernel<B2_BG_CLAMP>, prm));
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_kernel<B2_BG_ZERO>, prm));
+  }
+  return B2_OK;
+}
+
+}  // namespace b2
