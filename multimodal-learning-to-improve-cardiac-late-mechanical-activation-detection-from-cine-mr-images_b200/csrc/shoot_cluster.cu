@@ -80,8 +80,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         const int lr = k * RBc + br;
         Zs[(size_t)(r0 + lr) * W + c] = z[lr * kLDR + c];
       }
-      __threadfence();
-      cluster.sync();
+      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
       for (int i = tid; i < H * kSR; i += kCNT) {       // mirror-closed column group, all 256 rows
         const int r = i / kSR;
         z[r * kLDC + lc] = Zs[(size_t)r * W + pc];
@@ -120,8 +119,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         const int r = i / kSR;
         Zs[(size_t)r * W + pc] = z[r * kLDC + lc];
       }
-      __threadfence();
-      cluster.sync();
+      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br;
         z[lr * kLDR + c] = Zs[(size_t)(r0 + lr) * W + c];
@@ -191,8 +189,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
       }
       ucur = unext;
-      __threadfence();
-      cluster.sync();                                  // u_{s+1} of all four slabs visible to the cluster
+      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible                                  // u_{s+1} of all four slabs visible to the cluster
     }
 
     // ---- deformed source on the slab
@@ -213,8 +210,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
       unsigned int* cnts = reinterpret_cast<unsigned int*>(bins + ns);
       if (rk == 0)
         for (int i = tid; i < ns; i += kCNT) { bins[i] = 0ull; cnts[i] = 0u; }
-      __threadfence();
-      cluster.sync();
+      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
       const long long* mom = reinterpret_cast<const long long*>(a.moments) + 3 * b;
       const long long cnt = mom[0], sx = mom[1], sy = mom[2];
       float c0, c1;
@@ -238,8 +234,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         atomicAdd(bins + ksec, ecc_to_fixed(ecc));
         atomicAdd(cnts + ksec, 1u);
       }
-      __threadfence();
-      cluster.sync();
+      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
       if (rk == 0) {
         for (int k = tid; k < ns; k += kCNT) {
           const int cn = (int)__ldcg(cnts + k);
@@ -252,7 +247,6 @@ shoot_cluster_kernel(const ClusterParams prm) {
         }
       }
     }
-    __threadfence();
     cluster.sync();                                     // scratch free for the next pair of this cluster
   }
 }
