@@ -2,7 +2,7 @@
 """Secondary measurements for the other BASELINE.json configs (not the driver's bench line).
 
   python tools/bench_configs.py c3      # configs[2]: C2 batch + EPDiff adjoint backward (training-mode gradients)
-  python tools/bench_configs.py c4      # configs[3]: 256x256, 50 frames (op-level path), a shard of 16 slices
+  python tools/bench_configs.py c4      # configs[3]: 256x256, 50 frames (4-CTA cluster kernel; B2_NO_CLUSTER=1 = op-level path), a shard of 16 slices
 
 Prints one JSON line per config with pairs/s and the op-level roofline fraction.
 """
@@ -70,7 +70,7 @@ def main():
 
         ms = timed(step, 3, 1)
         nbytes = bytes_fwd
-        name = f"configs[3] shard: {B} slices x {T} frames 256x256 forward (op-level path)"
+        name = f"configs[3] shard: {B} slices x {T} frames 256x256 forward ({'op-level path' if os.environ.get('B2_NO_CLUSTER') else 'cluster kernel'})"
     ach = P * nbytes / (ms * 1e-3) / 1e9
     print(json.dumps({"config": name, "pairs": P, "ms_per_step": ms, "pairs_per_s": P / (ms * 1e-3),
                       "roofline": {"achieved_GBps": ach, "peak_GBps": peak, "frac": ach / peak,
