@@ -7,6 +7,7 @@
 Prints one JSON line per config with pairs/s and the op-level roofline fraction.
 """
 import json
+import os
 import pathlib
 import sys
 
