@@ -164,7 +164,12 @@ typedef struct b2_shoot_args {
   int32_t n_sectors, n_frames;
   int32_t background;
   float alpha, beta, gamma, T;
+  float* loss_terms;       /* optional output (P,2): per frame-pair {sum_x (tar - sdef)^2, sum_x vel . m0}, the two
+                              reductions of RegistrationReconstructionLoss (registration_losses.py:25-26) taken
+                              inside the shooting kernel (fixed summation order: bitwise reproducible).  Needs
+                              src and tar; on the op-level path (rectangular grids) also the sdef and vel outputs. */
 } b2_shoot_args;
+int64_t b2_sizeof_shoot_args(void);   /* ABI check for bindings that mirror the struct */
 
 int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps);
 int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t workspace_bytes, void* stream);
@@ -178,6 +183,27 @@ int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0, const flo
                  int num_steps, float alpha, float beta, float gamma, float T, int background,
                  int v0_is_momentum /* != 0: return dL/dm0 instead of dL/dv0 */,
                  void* workspace, int64_t workspace_bytes, void* stream);
+/* Same, plus the gradient of the regularisation term taken in closed form: with g_reg (P) = dL/d(sum_x vel . m0)
+ * per pair (NULL = none), d<sharp(m0), m0>/dm0 = 2 vel, hence gv0 += 2 g_reg[p] m0 (or, for v0_is_momentum,
+ * gm0 += 2 g_reg[p] vel with vel = v_0 of the trajectory) - no elementwise seed tensors, no extra FFT. */
+int b2_shoot_bwd_loss(const float* gu, const float* gvel, const float* gm0, const float* g_reg,
+                      const float* m0, const float* traj, float* gv0, int64_t P, int64_t H, int64_t W,
+                      int num_steps, float alpha, float beta, float gamma, float T, int background,
+                      int v0_is_momentum, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- loss epilogue of the path (RegistrationReconstructionLoss, registration_losses.py:22-28) ----
+ * Op-level form of b2_shoot_args.loss_terms: terms (P,2) = {sum_x (tar - sdef)^2, sum_x vel . m0} per pair from
+ * dense sdef, tar (P,1,H,W) and vel, m0 (P,2,H,W).  Either pair of inputs may be NULL (its term is 0). */
+int b2_recon_loss_terms(const float* sdef, const float* tar, const float* vel, const float* m0,
+                        float* terms, int64_t P, int64_t H, int64_t W, void* stream);
+/* Adjoint of sq[p] = sum_x (tar - interp(src, u))^2 without materialising sdef or its gradient image:
+ * recomputes sdef from the taps, du (+)= g_sq[p] * 2 (sdef - tar) * d sdef/du  (accumulate != 0 adds to du),
+ * dsrc (optional, zero-filled by the call; (B,1,H,W) or (P,1,H,W) with src_per_pair) receives the splat.
+ * src / tar addressing as in b2_shoot_args (slice strides; 0 = dense). */
+int b2_warp_sqerr_bwd(const float* g_sq, const float* src, const float* tar, const float* u,
+                      float* du, float* dsrc, int64_t B, int64_t T1, int64_t H, int64_t W,
+                      int src_per_pair, int64_t src_slice_stride, int64_t tar_slice_stride,
+                      int background, int accumulate, void* stream);
 
 /* Device properties the host side needs for grid sizing / reporting. */
 int b2_device_sm_count(int device);

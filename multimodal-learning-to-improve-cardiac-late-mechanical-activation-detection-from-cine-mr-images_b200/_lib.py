@@ -34,6 +34,7 @@ class ShootArgs(C.Structure):
         ("num_steps", C.c_int32), ("src_per_pair", C.c_int32), ("v0_is_momentum", C.c_int32),
         ("n_sectors", C.c_int32), ("n_frames", C.c_int32), ("background", C.c_int32),
         ("alpha", C.c_float), ("beta", C.c_float), ("gamma", C.c_float), ("T", C.c_float),
+        ("loss_terms", C.c_void_p),
     ]
 
 
@@ -64,6 +65,12 @@ SIGNATURES = {
     "b2_shoot_bwd_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "b2_shoot_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_float, c_float, c_float,
                              c_float, c_int, c_int, c_f, c_i64, c_f]),
+    "b2_sizeof_shoot_args": (c_i64, []),
+    "b2_shoot_bwd_loss": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_float, c_float,
+                                  c_float, c_float, c_int, c_int, c_f, c_i64, c_f]),
+    "b2_recon_loss_terms": (c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_f]),
+    "b2_warp_sqerr_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
+                                  c_int, c_int, c_f]),
     "b2_device_sm_count": (c_int, [c_int]),
 }
 
@@ -85,6 +92,9 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if L.b2_sizeof_shoot_args() != C.sizeof(ShootArgs):
+            raise RuntimeError(f"{_LIB_PATH}: b2_shoot_args is {L.b2_sizeof_shoot_args()} bytes in the library, "
+                               f"{C.sizeof(ShootArgs)} in the binding - rebuild with `python __graft_entry__.py`")
         _lib = L
     return _lib
 

@@ -26,6 +26,33 @@ constexpr int kMaxGridY = 65535;
 __host__ __device__ inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
 
 // ---------------------------------------------------------------------------
+// Deterministic CTA reduction of two float accumulators (loss epilogue): xor-tree inside each warp, one
+// partial per warp in `red` (2 * 32 floats of shared memory), xor-tree over the partials in warp 0.
+// Fixed order -> bitwise reproducible.  Result valid in thread 0.  Ends with the partials consumed; callers
+// synchronise before reusing `red`.
+// ---------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, int tid) {
+  static_assert(NT % 32 == 0 && NT <= 1024, "whole warps");
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = b; }
+  __syncthreads();
+  if (tid < 32) {
+    a = tid < NT / 32 ? red[tid] : 0.f;
+    b = tid < NT / 32 ? red[32 + tid] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Bilinear taps (A.1).  Indices are background-ruled independently; weights are
 // never renormalised.  v00=(i,j) v10=(i+1,j) v01=(i,j+1) v11=(i+1,j+1).
 // ---------------------------------------------------------------------------

@@ -59,13 +59,14 @@ template <int H, int W>
 struct ShootSmem {
   using FS = FluidSmem<H, W>;
   static constexpr size_t bins_off = (FS::bytes + 15) & ~size_t(15);
-  static constexpr size_t bytes = bins_off + sizeof(int32_t) * 5 * kFusedMaxSectors;
+  static constexpr size_t red_off = bins_off + sizeof(int32_t) * 5 * kFusedMaxSectors;   // loss-epilogue partials
+  static constexpr size_t bytes = red_off + sizeof(float) * 64;
 };
 
 // Thread <-> pixel map of every per-pixel phase: a thread keeps ONE column c = tid % W and walks the
 // rows r = tid / W, + RB, + 2 RB ... (RB = NT / W rows per band), so lanes run along the contiguous axis
 // (coalesced global rows, conflict-free smem rows) and all addresses advance by constants.
-template <int H, int W, int NT, int BG>
+template <int H, int W, int NT, int BG, bool LOSS>
 __global__ void __launch_bounds__(NT)
 shoot_fwd_kernel(const ShootParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -79,6 +80,7 @@ shoot_fwd_kernel(const ShootParams prm) {
   unsigned long long* sums_s = reinterpret_cast<unsigned long long*>(smem_raw + ShootSmem<H, W>::bins_off);
   int32_t* tab_s = reinterpret_cast<int32_t*>(sums_s + n_sectors);
   int* cnts_s = tab_s + 2 * n_sectors;
+  float* red_s = reinterpret_cast<float*>(smem_raw + ShootSmem<H, W>::red_off);
   const int tid = threadIdx.x;
   const int c = tid % W, br = tid / W;
   const int S = a.num_steps;
@@ -177,6 +179,7 @@ shoot_fwd_kernel(const ShootParams prm) {
       if (s == 0) {
         float* utraj0 = a.traj ? a.traj + ((size_t)p) * prm.field : nullptr;
         float* velout = a.vel ? a.vel + (size_t)p * prm.field : nullptr;
+        float acc_vm = 0.f;
 #pragma unroll 2
         for (int k = 0; k < NB; ++k) {
           const int r = k * RB + br, i = r * W + c;
@@ -188,6 +191,14 @@ shoot_fwd_kernel(const ShootParams prm) {
           if (utraj0) { utraj0[i] = 0.f; utraj0[N + i] = 0.f; }
           if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
           if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+          if (LOSS) acc_vm += v.x * m0g[i] + v.y * m0g[N + i];
+        }
+        if (LOSS) {
+          // loss epilogue, regularisation term sum vel . m0: reduced and written here so that no accumulator
+          // lives across the geodesic (64-register budget of the 1024-thread CTA)
+          float none = 0.f;
+          block_reduce2<NT>(acc_vm, none, red_s, tid);
+          if (tid == 0) a.loss_terms[2 * p + 1] = acc_vm;
         }
       } else {
 #pragma unroll (kComposeUnroll)
@@ -209,21 +220,36 @@ shoot_fwd_kernel(const ShootParams prm) {
     }
 
     // ---- deformed_source = interp(src, u^S)
-    if (a.sdef) {
+    if (a.sdef || LOSS) {
       // Lagrangian split: one source image per slice; Eulerian split (src_per_pair): one per pair, either
       // dense (P,1,H,W) or frames of a strided cine volume (slice stride given)
       const float* src = a.src_per_pair
                              ? (a.src_slice_stride ? a.src + (size_t)b * a.src_slice_stride + (size_t)t * N
                                                    : a.src + (size_t)p * N)
                              : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
-      float* sd = a.sdef + (size_t)p * N;
+      float* sd = a.sdef ? a.sdef + (size_t)p * N : nullptr;
+      const float* tarp = nullptr;
+      if (LOSS)
+        tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N : a.tar + (size_t)p * N;
+      float acc_sq = 0.f;
 #pragma unroll 2
       for (int k = 0; k < NB; ++k) {
         const int r = k * RB + br;
         const float2 u = z[r * LD + c];
-        sd[r * W + c] = gather1_ldg<BG>(src, (float)r + u.x, (float)c + u.y, H, W);
+        const float val = gather1_ldg<BG>(src, (float)r + u.x, (float)c + u.y, H, W);
+        if (sd) sd[r * W + c] = val;
+        if (LOSS) {
+          const float d = __ldg(tarp + r * W + c) - val;
+          acc_sq += d * d;
+        }
+      }
+      if (LOSS) {
+        float none = 0.f;
+        block_reduce2<NT>(acc_sq, none, red_s, tid);
+        if (tid == 0) a.loss_terms[2 * p] = acc_sq;
       }
     }
+
     // ---- strain matrix column t of slice b
     if (a.S) {
       for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0ull; cnts_s[i] = 0; }
@@ -247,9 +273,9 @@ struct FusedCfg {
     if (cached) return cached;
     const size_t smem = ShootSmem<H, W>::bytes;
     int per = 0;
-    if (cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP>, NT, smem) !=
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP, false>, NT, smem) !=
             cudaSuccess ||
         per < 1) {
       (void)cudaGetLastError();   // no device / query failed: fall back to the shared-memory bound
@@ -294,18 +320,24 @@ static int64_t fused_grid(int64_t P, int64_t H) {
   return g < P ? g : P;
 }
 
-template <int H, int W, int NT>
-static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
+template <int H, int W, int NT, int BG, bool LOSS>
+static int launch_fused_variant(const ShootParams& prm, int64_t grid, cudaStream_t st) {
   const size_t smem = ShootSmem<H, W>::bytes;
-  if (prm.a.background == B2_BG_CLAMP) {
-    B2_CUDA(cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    shoot_fwd_kernel<H, W, NT, B2_BG_CLAMP><<<(unsigned)grid, NT, smem, st>>>(prm);
-  } else {
-    B2_CUDA(cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    shoot_fwd_kernel<H, W, NT, B2_BG_ZERO><<<(unsigned)grid, NT, smem, st>>>(prm);
-  }
+  B2_CUDA(cudaFuncSetAttribute(shoot_fwd_kernel<H, W, NT, BG, LOSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  shoot_fwd_kernel<H, W, NT, BG, LOSS><<<(unsigned)grid, NT, smem, st>>>(prm);
   B2_CHECK_LAUNCH();
   return B2_OK;
+}
+
+// the loss epilogue is a compile-time variant: the inference kernel carries none of its branches
+template <int H, int W, int NT>
+static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
+  const bool loss = prm.a.loss_terms != nullptr;
+  if (prm.a.background == B2_BG_CLAMP)
+    return loss ? launch_fused_variant<H, W, NT, B2_BG_CLAMP, true>(prm, grid, st)
+                : launch_fused_variant<H, W, NT, B2_BG_CLAMP, false>(prm, grid, st);
+  return loss ? launch_fused_variant<H, W, NT, B2_BG_ZERO, true>(prm, grid, st)
+              : launch_fused_variant<H, W, NT, B2_BG_ZERO, false>(prm, grid, st);
 }
 
 #ifndef B2_BWD_U1
@@ -329,6 +361,7 @@ struct ShootBwdParams {
   const float* gu;      // dL/du^S   (P,2,H,W) or nullptr
   const float* gvel;    // dL/dvel   or nullptr
   const float* gm0;     // explicit dL/dm0 or nullptr
+  const float* g_reg;   // (P) dL/d(sum vel . m0) or nullptr: closed-form 2 g m0 (2 g vel) added to the result
   const float* m0;
   const float* traj;    // (S, 2, P, 2, H, W)
   float* gv0;
@@ -487,9 +520,13 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
     __syncthreads();
     if (!prm.v0_is_momentum) fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
     float* out = prm.gv0 + (size_t)p * prm.field;
+    // d<sharp(m0), m0>/dm0 = 2 vel and flat(2 vel) = 2 m0: the regularisation gradient needs no transform
+    const float g2 = prm.g_reg ? 2.f * __ldg(prm.g_reg + p) : 0.f;
+    const float* radd = prm.v0_is_momentum ? prm.traj + ((size_t)P + p) * prm.field : m0p;   // v_0 of the trajectory
     for (int k = 0; k < NB; ++k) {
       const int r = k * RB + br, i = r * W + c;
-      const float2 v = z[r * LD + c];
+      float2 v = z[r * LD + c];
+      if (prm.g_reg) { v.x += g2 * __ldg(radd + i); v.y += g2 * __ldg(radd + N + i); }
       out[i] = v.x;
       out[N + i] = v.y;
     }
@@ -517,6 +554,15 @@ static int launch_fused_bwd(const ShootBwdParams& prm, int background, cudaStrea
 }
 
 // ------------------------------------------------------------------ small elementwise helpers
+// y[p, :] += 2 g[p] x[p, :]   (closed-form regularisation gradient on the op-level path)
+__global__ void add_scaled_pairs_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ g,
+                                        int64_t P, int field) {
+  for (int64_t p = blockIdx.y; p < P; p += gridDim.y) {
+    const float g2 = 2.f * __ldg(g + p);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < field; i += gridDim.x * blockDim.x)
+      y[(size_t)p * field + i] += g2 * __ldg(x + (size_t)p * field + i);
+  }
+}
 __global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = a * x[i] + b * y[i];
@@ -552,6 +598,7 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   if (a.num_steps < 1 || a.num_steps > 4096 || !(a.gamma > 0.f) || a.alpha < 0.f || a.beta < 0.f || !(a.T > 0.f)) return B2_E_PARAM;
   if (a.background != B2_BG_CLAMP && a.background != B2_BG_ZERO) return B2_E_PARAM;
   if (a.sdef && !a.src) return B2_E_NULL;
+  if (a.loss_terms && (!a.src || !a.tar)) return B2_E_NULL;
   if (a.S && (!a.tar || !a.moments || !a.table)) return B2_E_NULL;
   if (a.S && (a.n_sectors < 3 || a.n_sectors > kFusedMaxSectors || a.n_frames < 1)) return B2_E_PARAM;
   const int64_t P = a.B * a.T1, H = a.H, W = a.W, field = 2 * H * W;
@@ -585,6 +632,7 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
 
   // ---- path B: op-level sequence
   if (a.src_slice_stride || a.tar_slice_stride) return B2_E_PARAM;   // strided volumes: fused path only
+  if (a.loss_terms && (!a.sdef || !a.vel)) return B2_E_NULL;         // the op-level reduction reads both outputs
   if (b2_fluid_workspace_bytes(P, H, W) <= 0) return B2_E_FFTSIZE;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   const size_t fbytes = align256(sizeof(float) * (size_t)P * field);
@@ -631,8 +679,13 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
                                      a.n_frames, stream))
       return e;
   }
+  if (a.loss_terms) {
+    if (int e = b2_recon_loss_terms(a.sdef, a.tar, a.vel, m0, a.loss_terms, P, H, W, stream)) return e;
+  }
   return B2_OK;
 }
+
+extern "C" int64_t b2_sizeof_shoot_args(void) { return (int64_t)sizeof(b2_shoot_args); }
 
 extern "C" int64_t b2_shoot_bwd_workspace_bytes(int64_t P, int64_t H, int64_t W) {
   if (P <= 0 || H <= 0 || W <= 0) return 0;
@@ -644,6 +697,14 @@ extern "C" int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0
                             float* gv0, int64_t P, int64_t H, int64_t W, int num_steps, float alpha, float beta,
                             float gamma, float T, int background, int v0_is_momentum, void* workspace,
                             int64_t workspace_bytes, void* stream) {
+  return b2_shoot_bwd_loss(gu, gvel, gm0, nullptr, m0, traj, gv0, P, H, W, num_steps, alpha, beta, gamma, T, background,
+                           v0_is_momentum, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b2_shoot_bwd_loss(const float* gu, const float* gvel, const float* gm0, const float* g_reg,
+                                 const float* m0, const float* traj, float* gv0, int64_t P, int64_t H, int64_t W,
+                                 int num_steps, float alpha, float beta, float gamma, float T, int background,
+                                 int v0_is_momentum, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!m0 || !traj || !gv0) return B2_E_NULL;
   if (P <= 0 || H < 2 || W < 2 || P > ((int64_t)1 << 30)) return B2_E_SHAPE;
   if (num_steps < 1 || !(gamma > 0.f) || !(T > 0.f)) return B2_E_PARAM;
@@ -651,7 +712,7 @@ extern "C" int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0
   cudaStream_t st = (cudaStream_t)stream;
   if (fused_size(H, W) && !getenv("B2_BWD_OPLEVEL")) {
     // path A: one persistent kernel; scratch = (resident CTAs) x 4 fields <= 5 P fields of the op-level layout
-    ShootBwdParams prm{gu, gvel, gm0, m0, traj, gv0, reinterpret_cast<float*>(workspace), P, 2 * H * W,
+    ShootBwdParams prm{gu, gvel, gm0, g_reg, m0, traj, gv0, reinterpret_cast<float*>(workspace), P, 2 * H * W,
                        num_steps, v0_is_momentum, alpha, beta, gamma, T};
     switch ((int)H) {
       case 16: return launch_fused_bwd<16, 16, 128>(prm, background, st);
@@ -695,12 +756,23 @@ extern "C" int b2_shoot_bwd(const float* gu, const float* gvel, const float* gm0
       if (int e = adstar_bwd_impl(g_v, u_s, m0, g_u, g_m0, wbuf, P, H, W, background, /*zero_dm0=*/false, st, g_uc)) return e;
     }
   }
+  const int field = (int)(2 * H * W);
+  dim3 rgrid((unsigned)((field + 255) / 256 < 64 ? (field + 255) / 256 : 64), (unsigned)(P < kMaxGridY ? P : kMaxGridY), 1);
   if (v0_is_momentum) {   // the input was m0 itself: return dL/dm0
     B2_CUDA(cudaMemcpyAsync(gv0, g_m0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    if (g_reg) {          // + 2 g vel, vel = v_0 of the trajectory
+      add_scaled_pairs_kernel<<<rgrid, 256, 0, st>>>(gv0, traj + n, g_reg, P, field);
+      B2_CHECK_LAUNCH();
+    }
     return B2_OK;
   }
   // dL/dv0 = flat(dL/dm0)
-  return fluid_apply_impl(g_m0, gv0, P, H, W, alpha, beta, gamma, 0, fws, fws_bytes, st);
+  if (int e = fluid_apply_impl(g_m0, gv0, P, H, W, alpha, beta, gamma, 0, fws, fws_bytes, st)) return e;
+  if (g_reg) {
+    add_scaled_pairs_kernel<<<rgrid, 256, 0, st>>>(gv0, m0, g_reg, P, field);
+    B2_CHECK_LAUNCH();
+  }
+  return B2_OK;
 }
 
 extern "C" int b2_device_sm_count(int device) {

@@ -32,7 +32,69 @@ struct ClusterParams {
 
 __device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? (q < 2 ? q : 5 - q) : (q ^ 1); }
 
-template <int BG>
+// One fluid operator on the slab in z (row layout in, row layout out): row FFT -> spectrum exchange through the
+// per-cluster L2 scratch Zs -> column FFT of a mirror-closed column group -> multiplier -> inverse, same way back.
+// A plain inlined function (a by-reference lambda put its closure in local memory).
+template <bool inverse>
+__device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2* __restrict__ z, const float2* tw,
+                                              const float2* cs, float2* Zs, const FluidParams fp, const int tid,
+                                              const int rk, const int r0, const int c, const int br, const int lc,
+                                              const int q, const int pc) {
+  constexpr int H = kCH, W = kCW, RBc = kCNT / kCW, NBc = kSR / RBc;
+  fft_lines<256, kSR, -1, kCNT, 1, kLDR>(z, tw, tid);
+  for (int k = 0; k < NBc; ++k) {                   // slab -> L2 scratch (cell order along c)
+    const int lr = k * RBc + br;
+    Zs[(size_t)(r0 + lr) * W + c] = z[lr * kLDR + c];
+  }
+  cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
+  for (int i = tid; i < H * kSR; i += kCNT) {       // mirror-closed column group, all 256 rows
+    const int r = i / kSR;
+    z[r * kLDC + lc] = Zs[(size_t)r * W + pc];
+  }
+  __syncthreads();
+  fft_lines<256, kSR, -1, kCNT, kLDC, 1>(z, tw, tid);
+  {
+    const int k1 = cell_to_freq<256>(pc);
+    const int qcell = freq_to_cell<256>((W - k1) & (W - 1));
+    const int lc2 = mirror_q(rk, q) * 16 + (qcell & 15);
+    const float2 cs1 = cs[k1];
+    const float h = 0.5f * fp.scale, bs1 = fp.beta * cs1.y;
+    for (int k0 = tid / kSR; k0 <= H / 2; k0 += kCNT / kSR) {
+      const int pr = freq_to_cell<256>(k0), qr = freq_to_cell<256>((H - k0) & (H - 1));
+      if (pr == qr && pc > qcell) continue;
+      const float2 cs0 = cs[k0];
+      const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
+      const float L00 = lam + fp.beta * cs0.x, L11 = lam + fp.beta * cs1.x, L01 = cs0.y * bs1;
+      float A, Br, Bi;
+      if (inverse) {
+        const float idet = __fdividef(h, L00 * L11 - L01 * L01);
+        A = idet * (L11 + L00); Br = idet * (L11 - L00); Bi = -2.0f * idet * L01;
+      } else {
+        A = h * (L00 + L11); Br = h * (L00 - L11); Bi = 2.0f * h * L01;
+      }
+      float2* zp = z + pr * kLDC + lc;
+      float2* zq = z + qr * kLDC + lc2;
+      const float2 Z = *zp, Zq = *zq;
+      *zp = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
+      if (zp != zq) *zq = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
+    }
+    __syncthreads();
+  }
+  fft_lines<256, kSR, +1, kCNT, kLDC, 1>(z, tw, tid);
+  for (int i = tid; i < H * kSR; i += kCNT) {
+    const int r = i / kSR;
+    Zs[(size_t)r * W + pc] = z[r * kLDC + lc];
+  }
+  cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
+  for (int k = 0; k < NBc; ++k) {
+    const int lr = k * RBc + br;
+    z[lr * kLDR + c] = Zs[(size_t)(r0 + lr) * W + c];
+  }
+  __syncthreads();
+  fft_lines<256, kSR, +1, kCNT, 1, kLDR>(z, tw, tid);
+}
+
+template <int BG, bool LOSS>
 __global__ void __launch_bounds__(kCNT)
 shoot_cluster_kernel(const ClusterParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -72,61 +134,8 @@ shoot_cluster_kernel(const ClusterParams prm) {
     float* m0g = (a.m0 && !a.v0_is_momentum) ? a.m0 + (size_t)p * 2 * N : m0s;
     const float* m0r = a.v0_is_momentum ? v0p : m0g;
     float* uout = a.u + (size_t)p * 2 * N;
+    float* lpart = reinterpret_cast<float*>(bins) + 3 * kMaxSectors;   // 4 x {sq, vm} partials of the loss epilogue
 
-    // one fluid operator on the slab in z (row layout in, row layout out)
-    auto fluid = [&](bool inverse) {
-      fft_lines<256, kSR, -1, kCNT, 1, kLDR>(z, tw, tid);
-      for (int k = 0; k < NBc; ++k) {                   // slab -> L2 scratch (cell order along c)
-        const int lr = k * RBc + br;
-        Zs[(size_t)(r0 + lr) * W + c] = z[lr * kLDR + c];
-      }
-      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
-      for (int i = tid; i < H * kSR; i += kCNT) {       // mirror-closed column group, all 256 rows
-        const int r = i / kSR;
-        z[r * kLDC + lc] = Zs[(size_t)r * W + pc];
-      }
-      __syncthreads();
-      fft_lines<256, kSR, -1, kCNT, kLDC, 1>(z, tw, tid);
-      {
-        const int k1 = cell_to_freq<256>(pc);
-        const int qcell = freq_to_cell<256>((W - k1) & (W - 1));
-        const int lc2 = mirror_q(rk, q) * 16 + (qcell & 15);
-        const float2 cs1 = cs[k1];
-        const float h = 0.5f * fp.scale, bs1 = fp.beta * cs1.y;
-        for (int k0 = tid / kSR; k0 <= H / 2; k0 += kCNT / kSR) {
-          const int pr = freq_to_cell<256>(k0), qr = freq_to_cell<256>((H - k0) & (H - 1));
-          if (pr == qr && pc > qcell) continue;
-          const float2 cs0 = cs[k0];
-          const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
-          const float L00 = lam + fp.beta * cs0.x, L11 = lam + fp.beta * cs1.x, L01 = cs0.y * bs1;
-          float A, Br, Bi;
-          if (inverse) {
-            const float idet = __fdividef(h, L00 * L11 - L01 * L01);
-            A = idet * (L11 + L00); Br = idet * (L11 - L00); Bi = -2.0f * idet * L01;
-          } else {
-            A = h * (L00 + L11); Br = h * (L00 - L11); Bi = 2.0f * h * L01;
-          }
-          float2* zp = z + pr * kLDC + lc;
-          float2* zq = z + qr * kLDC + lc2;
-          const float2 Z = *zp, Zq = *zq;
-          *zp = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
-          if (zp != zq) *zq = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
-        }
-        __syncthreads();
-      }
-      fft_lines<256, kSR, +1, kCNT, kLDC, 1>(z, tw, tid);
-      for (int i = tid; i < H * kSR; i += kCNT) {
-        const int r = i / kSR;
-        Zs[(size_t)r * W + pc] = z[r * kLDC + lc];
-      }
-      cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
-      for (int k = 0; k < NBc; ++k) {
-        const int lr = k * RBc + br;
-        z[lr * kLDR + c] = Zs[(size_t)(r0 + lr) * W + c];
-      }
-      __syncthreads();
-      fft_lines<256, kSR, +1, kCNT, 1, kLDR>(z, tw, tid);
-    };
 
     // ---- load v0 (or m0) slab, m0 = flat(v0)
     for (int k = 0; k < NBc; ++k) {
@@ -135,7 +144,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
     }
     __syncthreads();
     if (!a.v0_is_momentum) {
-      fluid(false);
+      cluster_fluid<false>(cluster, z, tw, cs, Zs, fp, tid, rk, r0, c, br, lc, q, pc);
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, i = (r0 + lr) * W + c;
         const float2 v = z[lr * kLDR + c];
@@ -165,7 +174,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         }
         __syncthreads();
       }
-      fluid(true);                                     // v = sharp(m), slab in z
+      cluster_fluid<true>(cluster, z, tw, cs, Zs, fp, tid, rk, r0, c, br, lc, q, pc);                                     // v = sharp(m), slab in z
       float* unext = (((S - (s + 1)) & 1) == 0) ? uout : ((s & 1) ? ubuf1 : ubuf0);
       if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * prm.P + p) * 2 * N : uout;
       float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * prm.P + p) * 2 * N : nullptr;
@@ -188,22 +197,50 @@ shoot_cluster_kernel(const ClusterParams prm) {
         if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
         if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
       }
+      if (LOSS && s == 0) {
+        // loss epilogue, regularisation term of this slab: v_0 . m0 (v_0 = vel just stored); reduced here so that no
+        // accumulator lives across the geodesic.  z still holds v and is not written before the next barrier.
+        float acc_vm = 0.f, none = 0.f;
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = k * RBc + br, i = (r0 + lr) * W + c;
+          const float2 v = z[lr * kLDR + c];
+          acc_vm += v.x * m0r[i] + v.y * m0r[N + i];
+        }
+        block_reduce2<kCNT>(acc_vm, none, reinterpret_cast<float*>(cs + 256), tid);
+        if (tid == 0) lpart[2 * rk + 1] = acc_vm;
+      }
       ucur = unext;
       cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible                                  // u_{s+1} of all four slabs visible to the cluster
     }
 
     // ---- deformed source on the slab
-    if (a.sdef) {
+    if (a.sdef || LOSS) {
       const float* src = a.src_per_pair
                              ? (a.src_slice_stride ? a.src + (size_t)b * a.src_slice_stride + (size_t)t * N
                                                    : a.src + (size_t)p * N)
                              : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
-      float* sd = a.sdef + (size_t)p * N;
+      float* sd = a.sdef ? a.sdef + (size_t)p * N : nullptr;
+      const float* tarp = nullptr;
+      if (LOSS)
+        tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N : a.tar + (size_t)p * N;
+      float acc_sq = 0.f;
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
-        sd[i] = gather1_ldg<BG>(src, (float)r + ucur[i], (float)c + ucur[N + i], H, W);
+        const float val = gather1_ldg<BG>(src, (float)r + ucur[i], (float)c + ucur[N + i], H, W);
+        if (sd) sd[i] = val;
+        if (LOSS) {
+          const float d = __ldg(tarp + i) - val;
+          acc_sq += d * d;
+        }
+      }
+      if (LOSS) {
+        // slab partials in fixed order; rank 0 adds the four after the closing cluster barrier
+        float none = 0.f;
+        block_reduce2<kCNT>(acc_sq, none, reinterpret_cast<float*>(cs + 256), tid);
+        if (tid == 0) lpart[2 * rk] = acc_sq;
       }
     }
+
     // ---- strain: every CTA bins its slab into the per-pair bins in L2 (integer atomics), rank 0 writes the column
     if (a.S) {
       const int ns = a.n_sectors;
@@ -248,16 +285,20 @@ shoot_cluster_kernel(const ClusterParams prm) {
       }
     }
     cluster.sync();                                     // scratch free for the next pair of this cluster
+    if (LOSS && rk == 0 && tid == 0) {
+      a.loss_terms[2 * p] = ((__ldcg(lpart) + __ldcg(lpart + 2)) + __ldcg(lpart + 4)) + __ldcg(lpart + 6);
+      a.loss_terms[2 * p + 1] = ((__ldcg(lpart + 1) + __ldcg(lpart + 3)) + __ldcg(lpart + 5)) + __ldcg(lpart + 7);
+    }
   }
 }
 
-constexpr size_t kClusterSmem = sizeof(float2) * ((size_t)kCH * kLDC + 512);
+constexpr size_t kClusterSmem = sizeof(float2) * ((size_t)kCH * kLDC + 512 + 32);   // z + twiddles + symbol LUT + reduction scratch
 
 static size_t cluster_scratch_floats() { return (size_t)8 * kCN + 4 * kMaxSectors; }   // Zs(2) + u(2x2) + m0(2) fields + bins
 
 template <int BG>
 static int cluster_max_active(int* out) {
-  B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<BG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kCL * 64);
   cfg.blockDim = dim3(kCNT);
@@ -268,7 +309,7 @@ static int cluster_max_active(int* out) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  B2_CUDA(cudaOccupancyMaxActiveClusters(&n, shoot_cluster_kernel<BG>, &cfg));
+  B2_CUDA(cudaOccupancyMaxActiveClusters(&n, shoot_cluster_kernel<BG, false>, &cfg));
   *out = n;
   return B2_OK;
 }
@@ -309,13 +350,19 @@ int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t s
   attr[0].val.clusterDim.x = kCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#define B2_CLUSTER_LAUNCH(BGV, LV)                                                                              \
+  do {                                                                                                          \
+    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<BGV, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 (int)kClusterSmem));                                                           \
+    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_kernel<BGV, LV>, prm));                                      \
+  } while (0)
+  const bool loss = a.loss_terms != nullptr;   // compile-time variant: the inference kernel carries no epilogue code
   if (a.background == B2_BG_CLAMP) {
-    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_kernel<B2_BG_CLAMP>, prm));
+    if (loss) B2_CLUSTER_LAUNCH(B2_BG_CLAMP, true); else B2_CLUSTER_LAUNCH(B2_BG_CLAMP, false);
   } else {
-    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_kernel<B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_kernel<B2_BG_ZERO>, prm));
+    if (loss) B2_CLUSTER_LAUNCH(B2_BG_ZERO, true); else B2_CLUSTER_LAUNCH(B2_BG_ZERO, false);
   }
+#undef B2_CLUSTER_LAUNCH
   return B2_OK;
 }
 

@@ -72,6 +72,7 @@ class JointRegisterStrainMatNet(nn.Module):
         self.sigma = float(config.get("sigma", 0.03))
         self.smoothing = config.get("strainmat_smoothing_method", None)
         self.smoothing_rank = int(config.get("strainmat_smoothing_SVD_rank", 5))
+        self.fused_loss_terms = bool(config.get("fused_loss_terms", False))   # adds 'registration_loss_terms'
         self.metric = FluidMetric(config.get("fluid_params", (1.0, 0.1, 0.05)))
         self.velocity_net = VelocityNet(int(config.get("velocity_net_width", 16)),
                                         float(config.get("max_velocity", 3.0)))
@@ -79,7 +80,7 @@ class JointRegisterStrainMatNet(nn.Module):
     def forward(self, src, tar):
         """Pairwise contract: src, tar (P,1,H,W) -> displacement / velocity / momentum / deformed_source."""
         v0 = self.velocity_net(src, tar)
-        return shoot_warp_pairs(v0, src, tar, self.metric, self.num_steps)
+        return shoot_warp_pairs(v0, src, tar, self.metric, self.num_steps, loss_terms=self.fused_loss_terms)
 
     def forward_volume(self, src_vol, tar_vol):
         """src_vol, tar_vol (B,1,T-1,H,W) -> {'strain_matrix','deformed_source','velocity','momentum',...}."""
@@ -88,7 +89,8 @@ class JointRegisterStrainMatNet(nn.Module):
         # split, frame t under the Eulerian one (modules/data/__init__.py:108-113)
         v0 = self.velocity_net(src_vol.reshape(B * T1, C, H, W), tar_vol.reshape(B * T1, C, H, W))
         out = shoot_warp_strain(v0, src_vol, tar_vol, self.metric, self.num_steps,
-                                n_sectors=self.n_sectors, n_frames=self.n_strain_matrix_frames)
+                                n_sectors=self.n_sectors, n_frames=self.n_strain_matrix_frames,
+                                loss_terms=self.fused_loss_terms)
         if self.smoothing == "SVD":
             out["strain_matrix"] = svd_smooth(out["strain_matrix"], self.smoothing_rank)
         return out

@@ -45,6 +45,8 @@ def _alloc_outputs(P, B, T1, H, W, dev, want, v0_is_momentum, n_sectors, n_frame
     if want.get("S"):
         out["S"] = new(B, 1, n_sectors, n_frames)
         out["counts"] = torch.empty((B, n_sectors, T1), dtype=torch.int32, device=dev)
+    if want.get("loss_terms"):
+        out["loss_terms"] = new(P, 2)
     if save_traj:
         out["traj"] = new(num_steps, 2, P, 2, H, W)
     return out
@@ -63,7 +65,7 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
         (tar.data_ptr() if tar is not None else None)
     a.moments = moments.data_ptr() if moments is not None else None
     a.table = table.data_ptr() if table is not None else None
-    for k in ("m0", "vel", "u", "sdef", "S", "counts", "traj"):
+    for k in ("m0", "vel", "u", "sdef", "S", "counts", "traj", "loss_terms"):
         setattr(a, k, out[k].data_ptr() if k in out else None)
     a.B, a.T1, a.H, a.W = B, T1, H, W
     a.src_slice_stride, a.tar_slice_stride = int(src_slice_stride), int(tar_slice_stride)
@@ -76,19 +78,19 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
     if ws is None or ws.numel() < nbytes:
         ws = _workspace(nbytes, dev)
     check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), nbytes, stream()), "b2_shoot_fwd")
-    fused = (H == W and H in (16, 32, 64, 128))
+    fused = H == W and H in (16, 32, 64, 128, 256)   # one persistent kernel (256: one 4-CTA cluster per pair)
     _lib.count_launch(1 if fused else 3 + 3 * int(num_steps) + 2)   # path B: flat, 3 kernels per step, warp, strain
     return out
 
 
-def _shoot_bwd(gu, gvel, gm0, m0, traj, metric, num_steps, T, background, v0_is_momentum):
+def _shoot_bwd(gu, gvel, gm0, m0, traj, metric, num_steps, T, background, v0_is_momentum, g_reg=None):
     P, _, H, W = m0.shape
     gv0 = torch.empty_like(m0)
     nbytes = lib().b2_shoot_bwd_workspace_bytes(P, H, W)
     ws = _workspace(nbytes, m0.device)
-    check(lib().b2_shoot_bwd(ptr(gu), ptr(gvel), ptr(gm0), ptr(m0), ptr(traj), ptr(gv0), P, H, W, int(num_steps),
-                             metric.alpha, metric.beta, metric.gamma, float(T), int(background),
-                             int(v0_is_momentum), ptr(ws), nbytes, stream()), "b2_shoot_bwd")
+    check(lib().b2_shoot_bwd_loss(ptr(gu), ptr(gvel), ptr(gm0), ptr(g_reg), ptr(m0), ptr(traj), ptr(gv0), P, H, W,
+                                  int(num_steps), metric.alpha, metric.beta, metric.gamma, float(T), int(background),
+                                  int(v0_is_momentum), ptr(ws), nbytes, stream()), "b2_shoot_bwd_loss")
     _lib.count_launch(6 * int(num_steps) + 1)
     return gv0
 
@@ -146,16 +148,18 @@ class ShootWarpStrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, v0, src, tar, moments, table, metric, num_steps, T, background, n_sectors, n_frames, B, T1,
-                src_per_pair, with_strain, src_ss, tar_ss):
+                src_per_pair, with_strain, src_ss, tar_ss, with_loss=False):
         v0 = v0.contiguous()
         require_cuda(v0)
         require_cuda(src if src_ss == 0 else None, tar if tar_ss == 0 else None)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         out = _launch_shoot(v0, src, tar, moments if with_strain else None, table if with_strain else None, metric,
                             num_steps, T, background, n_sectors, n_frames, B, T1,
-                            {"m0": True, "vel": True, "sdef": True, "S": with_strain}, False, src_per_pair, need,
-                            src_slice_stride=src_ss, tar_slice_stride=tar_ss)
-        ctx.cfg = (metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain)
+                            {"m0": True, "vel": True, "sdef": True, "S": with_strain, "loss_terms": with_loss}, False,
+                            src_per_pair, need, src_slice_stride=src_ss, tar_slice_stride=tar_ss)
+        ctx.cfg = (metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain,
+                   src_ss, tar_ss)
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None in backward, not as zero tensors
         if need:
             ctx.save_for_backward(out["m0"], out["u"], out["traj"], src, tar, moments, table,
                                   out.get("counts", torch.empty(0, device=v0.device)))
@@ -164,30 +168,26 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         else:
             S = torch.zeros((B, 1, n_sectors, n_frames), device=v0.device)
             ctx.mark_non_differentiable(S)
-        return out["m0"], out["vel"], out["u"], out["sdef"], S
+        if with_loss:
+            lt = out["loss_terms"]
+        else:
+            lt = torch.zeros((0, 2), device=v0.device)
+            ctx.mark_non_differentiable(lt)
+        return out["m0"], out["vel"], out["u"], out["sdef"], S, lt
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gm0, gvel, gu, gsdef, gS):
+    def backward(ctx, gm0, gvel, gu, gsdef, gS, glt=None):
         m0, u, traj, src, tar, moments, table, counts = ctx.saved_tensors
-        metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain = ctx.cfg
+        metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain, src_ss, tar_ss = ctx.cfg
         P, _, H, W = m0.shape
-        # op-level adjoint kernels take dense batches
-        src_c = src.reshape(P, 1, H, W).contiguous() if src_per_pair else src.contiguous()
-        gu_tot = gu.contiguous().clone() if gu is not None else torch.zeros_like(u)
+        want_dsrc = ctx.needs_input_grad[1]
+        gu_tot = None          # dL/du^S, accumulated in place by the kernels where they support it
         dsrc = None
-        if gsdef is not None:
-            du = torch.empty_like(u)
-            want_dsrc = ctx.needs_input_grad[1]
-            dsrc = torch.empty_like(src_c) if want_dsrc else None
-            if src_per_pair:
-                check(lib().b2_interp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(dsrc), ptr(du), P, P, P, 1,
-                                          H, W, 1.0, background, stream()), "b2_interp_bwd")
-            else:
-                check(lib().b2_warp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(dsrc), ptr(du), B, T1, 1,
-                                        H, W, 1.0, background, stream()), "b2_warp_bwd")
-            _lib.count_launch()
-            gu_tot += du
+
+        def add(acc, x):
+            return x if acc is None else acc.add_(x)
+
         if with_strain and gS is not None:
             du = torch.empty_like(u)
             tar_c = tar.reshape(B, T1, H, W).contiguous()
@@ -195,13 +195,46 @@ class ShootWarpStrainFunction(torch.autograd.Function):
                                              ptr(counts), ptr(du), B, T1, H, W, n_sectors, n_frames, stream()),
                   "b2_strain_sector_bwd")
             _lib.count_launch()
-            gu_tot += du
+            gu_tot = du
+        g_reg = None
+        if glt is not None:
+            # loss epilogue: adjoint of sum (tar - interp(src,u))^2 straight from (src, tar, u) - strided volumes are
+            # read in place - and the closed-form regularisation gradient inside the adjoint kernel (g_reg)
+            g_sq = glt[:, 0].contiguous()
+            g_reg = glt[:, 1].contiguous()
+            acc = gu_tot is not None
+            if not acc:
+                gu_tot = torch.empty_like(u)
+            d2 = torch.empty((P if src_per_pair else B, 1, H, W), device=u.device) if want_dsrc else None
+            check(lib().b2_warp_sqerr_bwd(ptr(g_sq), ptr(src), ptr(tar), ptr(u), ptr(gu_tot), ptr(d2), B, T1, H, W,
+                                          int(src_per_pair), int(src_ss), int(tar_ss), background, int(acc), stream()),
+                  "b2_warp_sqerr_bwd")
+            _lib.count_launch()
+            dsrc = add(dsrc, d2) if d2 is not None else dsrc
+        if gsdef is not None:
+            # op-level adjoint kernels take dense batches
+            src_c = src.reshape(P, 1, H, W).contiguous() if src_per_pair else src.contiguous()
+            du = torch.empty_like(u)
+            d1 = torch.empty_like(src_c) if want_dsrc else None
+            if src_per_pair:
+                check(lib().b2_interp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(d1), ptr(du), P, P, P, 1,
+                                          H, W, 1.0, background, stream()), "b2_interp_bwd")
+            else:
+                check(lib().b2_warp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(d1), ptr(du), B, T1, 1,
+                                        H, W, 1.0, background, stream()), "b2_warp_bwd")
+            _lib.count_launch()
+            gu_tot = add(gu_tot, du)
+            dsrc = add(dsrc, d1) if d1 is not None else dsrc
+        if gu is not None:
+            gu_tot = gu.contiguous() if gu_tot is None else gu_tot.add_(gu)
         gv0 = None
         if ctx.needs_input_grad[0]:
             gv0 = _shoot_bwd(gu_tot, gvel.contiguous() if gvel is not None else None,
                              gm0.contiguous() if gm0 is not None else None, m0, traj, metric, num_steps, T,
-                             background, False)
-        return (gv0, dsrc) + (None,) * 15
+                             background, False, g_reg=g_reg)
+        if dsrc is not None:
+            dsrc = dsrc.reshape(src.shape)
+        return (gv0, dsrc) + (None,) * 16
 
 
 def _fused_size(H, W):
@@ -213,14 +246,17 @@ def _rows_dense(t):
 
 
 def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T=1.0, n_sectors=N_SECTORS,
-                      n_frames=40, background="clamp", with_strain=True):
+                      n_frames=40, background="clamp", with_strain=True, loss_terms=False):
     """Fused hot path for a batch of slices.
 
     v0: (B*T1, 2, H, W) initial velocities, slice-major; src_vol, tar_vol: (B,1,T1,H,W)
     (the outputs of ``split_vol_to_registration_pairs(..., 'Lagrangian', output_dim=3)``;
     only frame 0 of ``src_vol`` is read - the repeat is never materialised - and ``tar_vol`` may be the
     strided view ``vol[:, :, 1:]``: the kernel reads the cine volume in place).
-    Returns the dict ``forward_volume`` hands to the trainer plus 'displacement'.
+    Returns the dict ``forward_volume`` hands to the trainer plus 'displacement'.  With ``loss_terms=True`` the
+    dict also holds 'registration_loss_terms' (P,2) = per pair {sum (tar - Sdef)^2, sum v.m}: the two reductions of
+    RegistrationReconstructionLoss taken inside the shooting kernel (see :mod:`losses`); their backward needs no
+    seed tensors.
     """
     B, Cc, T1, H, W = tar_vol.shape
     if Cc != 1 or v0.shape != (B * T1, 2, H, W):
@@ -244,25 +280,31 @@ def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T
         tar = tar_vol.reshape(B * T1, 1, H, W).contiguous()
     moments = mask_moments(mask0.contiguous()) if with_strain else None
     table = sector_table(n_sectors, v0.device) if with_strain else None
-    m0, vel, u, sdef, S = ShootWarpStrainFunction.apply(
+    m0, vel, u, sdef, S, lt = ShootWarpStrainFunction.apply(
         v0, src, tar, moments, table, metric, int(num_steps), float(T), BG[background], int(n_sectors),
-        int(n_frames), B, T1, not shared, bool(with_strain), int(src_ss), int(tar_ss))
-    return {
+        int(n_frames), B, T1, not shared, bool(with_strain), int(src_ss), int(tar_ss), bool(loss_terms))
+    out = {
         "strain_matrix": S,
         "deformed_source": sdef.reshape(B, 1, T1, H, W),
         "velocity": vel,
         "momentum": m0,
         "displacement": u,
     }
+    if loss_terms:
+        out["registration_loss_terms"] = lt
+    return out
 
 
-def shoot_warp_pairs(v0, src, tar, metric: FluidMetric, num_steps=10, T=1.0, background="clamp"):
+def shoot_warp_pairs(v0, src, tar, metric: FluidMetric, num_steps=10, T=1.0, background="clamp", loss_terms=False):
     """Pairwise contract (/root/reference/modules/trainer/reg_trainer.py:45,222-225): src, tar (P,1,H,W)."""
     P, _, H, W = v0.shape
-    m0, vel, u, sdef, _ = ShootWarpStrainFunction.apply(
+    m0, vel, u, sdef, _, lt = ShootWarpStrainFunction.apply(
         v0, src.contiguous(), tar.contiguous(), None, None, metric, int(num_steps), float(T), BG[background], 3, 1,
-        P, 1, True, False, 0, 0)
-    return {"displacement": u, "velocity": vel, "momentum": m0, "deformed_source": sdef}
+        P, 1, True, False, 0, 0, bool(loss_terms))
+    out = {"displacement": u, "velocity": vel, "momentum": m0, "deformed_source": sdef}
+    if loss_terms:
+        out["registration_loss_terms"] = lt
+    return out
 
 
 class HostPipeline:

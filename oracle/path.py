@@ -83,6 +83,15 @@ def forward_volume(v0, src_vol, tar_vol, metric: FluidMetric, num_steps: int = 1
     }
 
 
+def registration_loss_terms(pred, tar):
+    """Per-pair sums behind the loss below: (P,2) = {sum (tar - Sdef)^2, sum v.m} (float64 accumulation)."""
+    Sdef = pred["deformed_source"]
+    P = pred["velocity"].shape[0]
+    sq = ((tar.reshape(P, -1).double() - Sdef.reshape(P, -1).double()) ** 2).sum(dim=1)
+    vm = (pred["velocity"].double() * pred["momentum"].double()).reshape(P, -1).sum(dim=1)
+    return torch.stack([sq, vm], dim=1)
+
+
 def registration_reconstruction_loss(pred, target, sigma=0.03, regularization_weight=0.1):
     """/root/reference/modules/loss/registration_losses.py:22-28."""
     Sdef = pred["deformed_source"]

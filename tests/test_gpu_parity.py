@@ -370,6 +370,117 @@ def test_loss_boundary_with_reference_formula(pkg, oracle, dev, golden):
     assert abs(lg - lc) < 1e-5 * abs(lc)
 
 
+@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 4), (2, 3, 128, 128, 5), (1, 3, 256, 256, 2), (2, 3, 64, 128, 3)])
+def test_loss_epilogue_terms(pkg, oracle, dev, cfg):
+    """Per-pair {sum (tar-Sdef)^2, sum v.m} taken inside the shooting kernels (single-CTA, 4-CTA cluster, op-level
+    path) vs the oracle's float64 sums of its own outputs; bitwise reproducible; same loss as the reference formula."""
+    B, T, H, W, S = cfg
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 41, 3.0)
+    ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S)
+    terms_c = oracle.path.registration_loss_terms(ref, tar_vol)
+    args = (v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS))
+    out = pkg.shoot_warp_strain(*args, num_steps=S, loss_terms=True)
+    terms_g = out["registration_loss_terms"]
+    assert terms_g.shape == (B * (T - 1), 2)
+    # the squared error of a warped BINARY mask moves with |du| in pixels: allow what the fp32 oracle itself shows
+    ref64 = oracle.forward_volume(v0.double(), src_vol.double(), tar_vol.double(), oracle.FluidMetric(PARAMS), S)
+    own = relerr(terms_c, oracle.path.registration_loss_terms(ref64, tar_vol.double()))
+    assert relerr(terms_g[:, 1], terms_c[:, 1]) < TOL, f"v.m: {relerr(terms_g[:, 1], terms_c[:, 1]):.2e}"
+    assert relerr(terms_g[:, 0], terms_c[:, 0]) < max(TOL, 3 * own), f"sq: {relerr(terms_g[:, 0], terms_c[:, 0]):.2e}"
+    # the kernel sums exactly what it wrote: op-level reduction of the GPU outputs agrees to fp32 summation error
+    t2 = torch.empty_like(terms_g)
+    P = B * (T - 1)
+    pkg._lib.check(pkg._lib.lib().b2_recon_loss_terms(
+        pkg._lib.ptr(out["deformed_source"].contiguous()), pkg._lib.ptr(args[2].contiguous()),
+        pkg._lib.ptr(out["velocity"]), pkg._lib.ptr(out["momentum"]), pkg._lib.ptr(t2), P, H, W, pkg._lib.stream()))
+    assert relerr(t2, terms_g) < 2e-6
+    # fixed summation order -> bitwise reproducible
+    again = pkg.shoot_warp_strain(*args, num_steps=S, loss_terms=True)["registration_loss_terms"]
+    assert torch.equal(again, terms_g)
+    # drop-in loss class: fused terms == the reference formula on the tensors
+    tgt = {"registration_target": args[2]}
+    fused = pkg.RegistrationReconstructionLoss(0.03, 0.1)(out, tgt)
+    plain = pkg.RegistrationReconstructionLoss(0.03, 0.1)({k: v for k, v in out.items() if k != "registration_loss_terms"}, tgt)
+    lc = oracle.registration_reconstruction_loss(ref, {"registration_target": tar_vol})
+    assert abs(fused.item() - plain.item()) < 1e-5 * abs(plain.item())
+    assert abs(fused.item() - float(lc)) < max(1e-5, 3 * own) * abs(float(lc))
+
+
+@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 4, "Lagrangian"), (2, 3, 64, 64, 3, "Eulerian"), (1, 3, 64, 128, 2, "Lagrangian")])
+def test_loss_epilogue_backward(pkg, oracle, dev, cfg):
+    """Gradient of the reference's training loss taken through the fused loss terms (b2_warp_sqerr_bwd + the
+    closed-form regularisation gradient in b2_shoot_bwd_loss) vs autograd through the oracle, and vs the unfused
+    product path (elementwise seeds)."""
+    B, T, H, W, S, split = cfg
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    src_vol, tar_vol = pkg.data.split_vol_to_registration_pairs(vol, split, 3)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 43, 2.0)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=44)
+
+    vc = v0.clone().requires_grad_(True)
+    oc = oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S)
+    lc = oracle.registration_reconstruction_loss(oc, {"registration_target": tar_vol}) \
+        + 1000.0 * torch.mean((oc["strain_matrix"] - Sgt) ** 2)
+    lc.backward()
+
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol.to(dev), split, 3)     # strided views of the volume
+    crit = pkg.RegistrationReconstructionLoss(0.03, 0.1)
+    grads = {}
+    for fused in (True, False):
+        vg = v0.to(dev).requires_grad_(True)
+        out = pkg.shoot_warp_strain(vg, sv, tv, pkg.FluidMetric(PARAMS), num_steps=S, loss_terms=fused)
+        lg = crit(out, {"registration_target": tv}) + 1000.0 * torch.mean((out["strain_matrix"] - Sgt.to(dev)) ** 2)
+        lg.backward()
+        assert abs(lg.item() - lc.item()) < 1e-4 * abs(lc.item())
+        grads[fused] = vg.grad
+        assert relerr(vg.grad, vc.grad) < 1e-4, f"fused={fused}: {relerr(vg.grad, vc.grad):.2e}"
+    assert relerr(grads[True], grads[False]) < 5e-5
+    # gradient w.r.t. the source image through the fused squared-error adjoint (dense pairwise form)
+    P = B * (T - 1)
+    srcp = src_vol.reshape(P, 1, H, W).contiguous()
+    tarp = tar_vol.reshape(P, 1, H, W).contiguous()
+    sc = srcp.clone().requires_grad_(True)
+    ocp = oracle.path.forward_pairs(v0, sc, tarp, oracle.FluidMetric(PARAMS), S)
+    ((tarp - ocp["deformed_source"]) ** 2).sum().backward()
+    sg = srcp.to(dev).requires_grad_(True)
+    og = pkg.shoot_warp_pairs(v0.to(dev), sg, tarp.to(dev), pkg.FluidMetric(PARAMS), num_steps=S, loss_terms=True)
+    og["registration_loss_terms"][:, 0].sum().backward()
+    assert relerr(sg.grad, sc.grad) < GTOL, f"dsrc {relerr(sg.grad, sc.grad):.2e}"
+
+
+def test_expmap_momentum_regulariser_gradient(pkg, oracle, dev):
+    """v0_is_momentum branch of b2_shoot_bwd_loss: d/dm0 of g * <sharp(m0), m0> = 2 g vel, added to the adjoint."""
+    import ctypes as C
+    H = W = 32
+    S, P = 3, 2
+    mc = oracle.FluidMetric(PARAMS)
+    m0 = mc.flat(_smooth_v0(pkg, P, H, W, 45, 2.0))
+    g_reg = torch.tensor([0.7, -1.3])
+    gu = 0.1 * _rand(P, 2, H, W, seed=46)
+    mr = m0.clone().requires_grad_(True)
+    u = oracle.expmap(mc, mr, num_steps=S)
+    ((u * gu).sum() + (g_reg.view(P, 1, 1, 1) * mc.sharp(mr) * mr).sum()).backward()
+    L = pkg._lib
+    md = m0.to(dev)
+    out = pkg.shooting._launch_shoot(md, None, None, None, None, pkg.FluidMetric(PARAMS), S, 1.0, 0, 3, 1, P, 1, {}, True,
+                                     False, True)
+    for oplevel in (False, True):
+        gm = torch.empty_like(md)
+        nbytes = L.lib().b2_shoot_bwd_workspace_bytes(P, H, W)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        import os
+        if oplevel:
+            os.environ["B2_BWD_OPLEVEL"] = "1"
+        try:
+            L.check(L.lib().b2_shoot_bwd_loss(L.ptr(gu.to(dev)), None, None, L.ptr(g_reg.to(dev)), L.ptr(md),
+                                              L.ptr(out["traj"]), L.ptr(gm), P, H, W, S, *PARAMS, 1.0, 0, 1, L.ptr(ws),
+                                              nbytes, L.stream()))
+        finally:
+            os.environ.pop("B2_BWD_OPLEVEL", None)
+        assert relerr(gm, mr.grad) < 5e-5, f"oplevel={oplevel}: {relerr(gm, mr.grad):.2e}"
+
+
 def test_models_forward_volume_on_gpu(pkg, dev):
     """models shim end to end: forward_volume -> LMA net -> backward, keys/shapes of the trainer contract."""
     torch.manual_seed(2434)

@@ -46,6 +46,20 @@ def test_align_frames_matches_reference(golden, oracle, pkg):
     assert np.array_equal(oracle.align_frames(S, 3).numpy(), golden["align_crop3"])
 
 
+def test_fused_loss_class_matches_reference(golden, oracle, pkg):
+    """The drop-in RegistrationReconstructionLoss (host logic of the loss epilogue): from tensors and from the
+    per-pair terms it reproduces the value the reference's own LossCalculator gave for the golden prediction."""
+    pred = {k[len("loss_pred_"):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("loss_pred_")}
+    target = {k[len("loss_target_"):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("loss_target_")}
+    want = float(golden["loss_part_registration_reconstruction"])
+    crit = pkg.RegistrationReconstructionLoss(float(golden["loss_sigma"]), float(golden["loss_reg_weight"]))
+    assert abs(crit(pred, target).item() - want) <= 1e-5 * abs(want)
+    terms = oracle.path.registration_loss_terms(pred, target["registration_target"])
+    assert terms.shape == (pred["velocity"].shape[0], 2)
+    fused = crit({**pred, "registration_loss_terms": terms.float()}, target)
+    assert abs(fused.item() - want) <= 1e-5 * abs(want)
+
+
 def test_loss_boundary_matches_reference(golden, oracle):
     pred = {k[len("loss_pred_"):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("loss_pred_")}
     target = {k[len("loss_target_"):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("loss_target_")}

@@ -2,6 +2,7 @@
 """Secondary measurements for the other BASELINE.json configs (not the driver's bench line).
 
   python tools/bench_configs.py c3      # configs[2]: C2 batch + EPDiff adjoint backward (training-mode gradients)
+  python tools/bench_configs.py c3f     # same with the fused loss epilogue (per-pair loss terms from the kernel)
   python tools/bench_configs.py c4      # configs[3]: 256x256, 50 frames (4-CTA cluster kernel; B2_NO_CLUSTER=1 = op-level path), a shard of 16 slices
 
 Prints one JSON line per config with pairs/s and the op-level roofline fraction.
@@ -40,7 +41,7 @@ def main():
     peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
     metric = pkg.FluidMetric(PARAMS)
     S = 10
-    if which == "c3":
+    if which in ("c3", "c3f"):
         B, T, H, W = 64, 25, 128, 128
     else:
         B, T, H, W = 16, 50, 256, 256
@@ -49,21 +50,22 @@ def main():
     v0 = pkg.synthetic.synthetic_v0(P, H, W, seed=5, max_disp=3.0).to(dev)
     src_vol, tar_vol = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
     bytes_fwd = 4 * (15 + 16 * S) * N
-    if which == "c3":
+    if which in ("c3", "c3f"):
         Sgt = torch.zeros(B, 1, 126, 40, device=dev)
         vg = v0.clone().requires_grad_(True)
+        fused = which == "c3f"            # loss epilogue: per-pair sums from the kernel, seedless adjoints
+        crit = pkg.RegistrationReconstructionLoss(0.03, 0.1)
 
         def step():
             vg.grad = None
-            out = pkg.shoot_warp_strain(vg, src_vol, tar_vol, metric, num_steps=S)
-            loss = 0.5 * torch.mean((tar_vol - out["deformed_source"]) ** 2) / 0.03 ** 2 \
-                + 0.1 * (out["velocity"] * out["momentum"]).sum() / tar_vol.numel() \
+            out = pkg.shoot_warp_strain(vg, src_vol, tar_vol, metric, num_steps=S, loss_terms=fused)
+            loss = crit(out, {"registration_target": tar_vol}) \
                 + 1000.0 * torch.mean((out["strain_matrix"] - Sgt) ** 2)
             loss.backward()
 
         ms = timed(step, 5, 2)
         nbytes = 3 * bytes_fwd
-        name = "configs[2]: C2 batch + EPDiff adjoint backward"
+        name = "configs[2]: C2 batch + EPDiff adjoint backward" + (" (fused loss epilogue)" if fused else "")
     else:
         def step():
             with torch.no_grad():
