@@ -205,6 +205,17 @@ int b2_warp_sqerr_bwd(const float* g_sq, const float* src, const float* tar, con
                       int src_per_pair, int64_t src_slice_stride, int64_t tar_slice_stride,
                       int background, int accumulate, void* stream);
 
+/* ---- augmentation in front of the path (modules/data/augmentation/affine.py:24-87, rotate then translate) ----
+ * vol, out (B,1,T,H,W).  xform (B,6) float64 on the device: per slice the inverse map of
+ * skimage.transform.rotate(mask, -n*360/126, order=0, resize=False): (col_in,row_in) = M (col_out,row_out,1),
+ * nearest neighbour, outside -> 0.  shift (B,2) int32 {translate_y, translate_x} (np.roll on rows / cols, applied
+ * after the rotation) or NULL.  Index selection in float64 without contraction: bit-exact against numpy. */
+int b2_augment_volume(const float* vol, float* out, const double* xform, const int32_t* shift,
+                      int64_t B, int64_t T, int64_t H, int64_t W, void* stream);
+/* out[b, (k + n[b]) mod R, :] = S[b, k, :]: np.roll(strain, n, axis=0) / np.roll(TOS, n) per sample
+ * (affine.py:74,78); S (B,R,C), n (B) int32 on the device. */
+int b2_roll_rows(const float* S, float* out, const int32_t* n, int64_t B, int64_t R, int64_t C, void* stream);
+
 /* Device properties the host side needs for grid sizing / reporting. */
 int b2_device_sm_count(int device);
 

@@ -6,7 +6,7 @@ jacobian_times_vectorfield / compose_disp_vel`` and the ``models`` package's
 ``build_model / forward_volume``); the arithmetic runs in hand-written sm_100a
 CUDA behind the C ABI of ``include/b2lddmm.h``.  No CPU fallback.
 """
-from . import _lib, data, losses, models, ops, parallel, shooting, strain, synthetic  # noqa: F401
+from . import _lib, augment, data, losses, models, ops, parallel, shooting, strain, synthetic  # noqa: F401
 from .losses import RegistrationReconstructionLoss, reconstruction_loss_from_terms  # noqa: F401
 from .models import JointRegisterStrainMatNet, NetStrainMat2LMA, build_model  # noqa: F401
 from .ops import (  # noqa: F401

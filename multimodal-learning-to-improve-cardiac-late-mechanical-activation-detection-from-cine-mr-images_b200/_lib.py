@@ -71,6 +71,8 @@ SIGNATURES = {
     "b2_recon_loss_terms": (c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_f]),
     "b2_warp_sqerr_bwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
                                   c_int, c_int, c_f]),
+    "b2_augment_volume": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f]),
+    "b2_roll_rows": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_f]),
     "b2_device_sm_count": (c_int, [c_int]),
 }
 
@@ -117,7 +119,7 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def require_cuda(*tensors, dtype=torch.float32):
+def require_cuda(*tensors, dtype=torch.float32):  # noqa: C901
     """All tensors must be contiguous CUDA tensors of one device (no CPU fallback)."""
     dev = None
     for t in tensors:

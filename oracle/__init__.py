@@ -50,3 +50,4 @@ from .path import (  # noqa: F401
     forward_pairs,
     registration_reconstruction_loss,
 )
+from . import augment, path  # noqa: F401,E402

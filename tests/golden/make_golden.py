@@ -18,7 +18,10 @@ are for the callers either side of it:
                                        /root/reference/modules/data/augmentation/affine.py:52-87
   (recorded as the constants it pins; skimage itself is not installed here).
 
-Outputs ``tests/golden/ref_boundary.npz`` (committed).
+* ``translate`` / ``rotate``           /root/reference/modules/data/augmentation/affine.py:24-87
+  (numpy parts as is; the skimage call is recorded through a stub: angle and keyword arguments).
+
+Outputs ``tests/golden/ref_boundary.npz`` and ``tests/golden/ref_augment.npz`` (committed).
 """
 import importlib.util
 import json
@@ -31,15 +34,21 @@ import torch
 
 REF = pathlib.Path("/root/reference")
 OUT = pathlib.Path(__file__).resolve().parent / "ref_boundary.npz"
+OUT_AUG = pathlib.Path(__file__).resolve().parent / "ref_augment.npz"
+SKROTATE_CALLS = []
 
 
 def _import_reference():
     # skimage is absent in this image; the functions we need never call it.
     sk = types.ModuleType("skimage")
     skt = types.ModuleType("skimage.transform")
-    skt.rotate = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("skimage stub"))
+    def _skrotate_stub(image, angle, **kw):
+        # skimage is not installed: record how the reference calls it and hand the image back unchanged
+        SKROTATE_CALLS.append((float(angle), dict(kw)))
+        return image
+    skt.rotate = _skrotate_stub
     skm = types.ModuleType("skimage.morphology")
-    skm.dilation = skt.rotate
+    skm.dilation = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("skimage stub"))
     sys.modules.setdefault("skimage", sk)
     sys.modules.setdefault("skimage.transform", skt)
     sys.modules.setdefault("skimage.morphology", skm)
@@ -110,6 +119,48 @@ def main():
 
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes, {len(out)} arrays)")
+    make_augment_golden()
+
+
+def make_augment_golden():
+    """translate / rotate of /root/reference/modules/data/augmentation/affine.py:24-87 on a synthetic datum.
+
+    ``translate`` is pure numpy and runs as is.  ``rotate`` calls skimage (absent): the stub records the angle and
+    keyword arguments the reference passes and returns the mask unchanged, so the golden pins the call convention
+    and the np.roll of the strain matrix / TOS curve, not skimage's resampling."""
+    from modules.data.augmentation import affine as ref_aff  # noqa: E402
+    rng = np.random.default_rng(2434)
+    H, W, T = 12, 10, 4
+    datum = {
+        "cine_lv_myo_masks_merged": (rng.random((H, W, T)) > 0.5).astype(np.float32),
+        "StrainInfo": {"CCmid": rng.standard_normal((126, 40)).astype(np.float32)},
+        "TOSAnalysis": {"TOSfullRes_Jerry": (rng.random(126) * 60).astype(np.float32)},
+    }
+    out = {"mask": datum["cine_lv_myo_masks_merged"], "strain": datum["StrainInfo"]["CCmid"],
+           "tos": datum["TOSAnalysis"]["TOSfullRes_Jerry"]}
+    shifts = [(0, 0), (3, -2), (-5, 7), (12, 10), (-13, 1)]
+    out["shifts"] = np.array(shifts, dtype=np.int64)
+    for i, (ty, tx) in enumerate(shifts):
+        d = ref_aff.translate(datum, ty, tx)
+        out[f"translate_{i}_mask"] = d["cine_lv_myo_masks_merged"]
+        out[f"translate_{i}_strain"] = d["StrainInfo"]["CCmid"]
+        out[f"translate_{i}_tos"] = d["TOSAnalysis"]["TOSfullRes_Jerry"]
+    ns = [0, 1, 5, -3, 126, 130]
+    out["rot_n"] = np.array(ns, dtype=np.int64)
+    angles = []
+    for i, n in enumerate(ns):
+        SKROTATE_CALLS.clear()
+        d = ref_aff.rotate(datum, n)
+        assert len(SKROTATE_CALLS) == 1, SKROTATE_CALLS
+        ang, kw = SKROTATE_CALLS[0]
+        assert kw == {"resize": False, "preserve_range": True, "order": 0}, kw
+        angles.append(ang)
+        out[f"rotate_{i}_strain"] = d["StrainInfo"]["CCmid"]
+        out[f"rotate_{i}_tos"] = d["TOSAnalysis"]["TOSfullRes_Jerry"]
+    out["rot_angle_degree"] = np.array(angles, dtype=np.float64)
+    out["skrotate_order"] = np.int64(0)
+    np.savez_compressed(OUT_AUG, **out)
+    print(f"wrote {OUT_AUG} ({OUT_AUG.stat().st_size} bytes, {len(out)} arrays)")
 
 
 if __name__ == "__main__":

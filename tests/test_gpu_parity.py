@@ -481,6 +481,65 @@ def test_expmap_momentum_regulariser_gradient(pkg, oracle, dev):
         assert relerr(gm, mr.grad) < 5e-5, f"oplevel={oplevel}: {relerr(gm, mr.grad):.2e}"
 
 
+@pytest.mark.parametrize("shape", [(3, 4, 128, 128), (2, 3, 256, 256), (4, 2, 33, 47), (1, 1, 2, 2)])
+def test_augment_volume_bit_exact(pkg, oracle, dev, shape):
+    """Device rotate(n sectors) + translate of a cine batch vs the numpy oracle: index selection is integer work."""
+    B, T, H, W = shape
+    rng = np.random.default_rng(11)
+    vol = rng.random((B, 1, T, H, W)).astype(np.float32)
+    ns = rng.integers(-130, 131, B)
+    ty = rng.integers(-2 * H, 2 * H, B)
+    tx = rng.integers(-2 * W, 2 * W, B)
+    ns[0], ty[0], tx[0] = 0, 0, 0
+    want = oracle.augment.rotate_translate_volume(vol, ns, ty, tx)
+    got = pkg.augment.rotate_translate_volume(torch.from_numpy(vol).to(dev), ns, ty, tx)
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+    assert torch.equal(got[0].cpu(), torch.from_numpy(vol[0]))            # identity transform
+    # rows of the strain matrix / TOS follow the rotation
+    S = rng.standard_normal((B, 1, 126, 40)).astype(np.float32)
+    tos = rng.random((B, 126)).astype(np.float32)
+    out = pkg.augment.augment_batch(torch.from_numpy(vol).to(dev), torch.from_numpy(S).to(dev),
+                                    torch.from_numpy(tos).to(dev), ns, ty, tx)
+    assert torch.equal(out["cine_myo_mask"], got)
+    assert np.array_equal(out["strain_matrix"].cpu().numpy(), oracle.augment.roll_rows(S, ns))
+    assert np.array_equal(out["TOS"].cpu().numpy(), oracle.augment.roll_rows(tos, ns))
+
+
+def test_augment_translate_matches_reference_golden(pkg, dev):
+    """Device translation against the output of the reference's own translate() (tests/golden/ref_augment.npz)."""
+    import pathlib
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_augment.npz")
+    vol = torch.from_numpy(np.ascontiguousarray(np.moveaxis(g["mask"], -1, 0)))[None, None].to(dev)
+    for i, (ty, tx) in enumerate(g["shifts"]):
+        got = pkg.augment.rotate_translate_volume(vol, 0, int(ty), int(tx))
+        assert np.array_equal(np.moveaxis(got[0, 0].cpu().numpy(), 0, -1), g[f"translate_{i}_mask"])
+    for i, n in enumerate(g["rot_n"]):
+        got = pkg.augment.roll_rows(torch.from_numpy(g["strain"])[None, None].to(dev), int(n))
+        assert np.array_equal(got[0, 0].cpu().numpy(), g[f"rotate_{i}_strain"])
+        got = pkg.augment.roll_rows(torch.from_numpy(g["tos"])[None].to(dev), int(n))
+        assert np.array_equal(got[0].cpu().numpy(), g[f"rotate_{i}_tos"])
+
+
+def test_augmented_batch_through_the_path(pkg, dev):
+    """Rotating the cine batch by n sectors rolls the rows of the strain matrix the path produces by n (the
+    equivariance the reference's augmentation assumes, affine.py:56-78).  n = 63 is a half turn, an exact index
+    permutation of the grid, so the identity holds to fp32 rounding; the velocity field is carried along."""
+    B, T, H, W, S = 2, 4, 128, 128, 5
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).to(dev)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 51, 2.0).to(dev)
+    n = 63
+    rot = pkg.augment.rotate_translate_volume(vol, n)
+    assert torch.equal(rot, vol.flip(-1, -2))
+    v_rot = -v0.flip(-1, -2)                                   # pushed forward by the point reflection
+    m = pkg.FluidMetric(PARAMS)
+    a = pkg.shoot_warp_strain(v0, *pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3), m, num_steps=S)
+    b = pkg.shoot_warp_strain(v_rot.contiguous(), *pkg.data.split_vol_to_registration_pairs(rot, "Lagrangian", 3), m,
+                              num_steps=S)
+    assert relerr(b["displacement"], -a["displacement"].flip(-1, -2)) < 1e-4
+    rolled = pkg.augment.roll_rows(a["strain_matrix"], n)
+    assert relerr(b["strain_matrix"], rolled) < 1e-3, f"{relerr(b['strain_matrix'], rolled):.2e}"
+
+
 def test_models_forward_volume_on_gpu(pkg, dev):
     """models shim end to end: forward_volume -> LMA net -> backward, keys/shapes of the trainer contract."""
     torch.manual_seed(2434)

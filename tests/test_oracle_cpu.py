@@ -293,3 +293,60 @@ def test_c_oracle_matches_torch(oracle, pkg, cfg):
     tab = (ctypes.c_int32 * 252)()
     c_oracle.lib().b2o_sector_table(126, tab)
     assert np.array_equal(np.array(list(tab)).reshape(126, 2), oracle.sector_boundaries(126))
+
+
+# ----------------------------------------------------------------- augmentation (reference affine.py)
+@pytest.fixture(scope="module")
+def aug_golden():
+    import pathlib
+    return np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_augment.npz")
+
+
+def test_augment_translate_matches_reference(aug_golden, oracle):
+    """np.roll translation of masks (H,W,T layout in the reference, (B,1,T,H,W) here); strain / TOS untouched."""
+    g = aug_golden
+    mask = g["mask"]                                           # (H,W,T)
+    vol = np.moveaxis(mask, -1, 0)[None, None]                 # (1,1,T,H,W)
+    for i, (ty, tx) in enumerate(g["shifts"]):
+        got = oracle.augment.rotate_translate_volume(vol, [0], [ty], [tx])
+        assert np.array_equal(np.moveaxis(got[0, 0], 0, -1), g[f"translate_{i}_mask"])
+        assert np.array_equal(g[f"translate_{i}_strain"], g["strain"]) and np.array_equal(g[f"translate_{i}_tos"], g["tos"])
+
+
+def test_augment_rotate_convention_matches_reference(aug_golden, oracle):
+    """Angle handed to skimage and the strain/TOS roll of affine.py:56,74,78; order=0 nearest neighbour."""
+    g = aug_golden
+    assert int(g["skrotate_order"]) == 0
+    for i, n in enumerate(g["rot_n"]):
+        assert oracle.augment.rotation_angle_degree(int(n)) == float(g["rot_angle_degree"][i])
+        assert np.array_equal(oracle.augment.roll_rows(g["strain"][None, None], [n])[0, 0], g[f"rotate_{i}_strain"])
+        assert np.array_equal(oracle.augment.roll_rows(g["tos"][None], [n])[0], g[f"rotate_{i}_tos"])
+
+
+def test_augment_rotation_properties(oracle, pkg):
+    """The restated skimage rotation: identity at n = 0 and n = 126, quarter turns are exact index permutations,
+    and rotating a mask by n sectors shifts the (integer) sector ids of its pixels by n - the equivariance
+    affine.py:56-78 relies on when it rolls the strain rows."""
+    rng = np.random.default_rng(7)
+    img = rng.random((3, 16, 16)).astype(np.float32)
+    A = oracle.augment
+    for n in (0, 126, -126):
+        assert np.array_equal(A.rotate_nearest(img, A.rotate_matrix(A.rotation_angle_degree(n), 16, 16)), img)
+    # skimage's angle is counter-clockwise on the displayed image: +90 deg == np.rot90(k=1) for a square image
+    assert np.array_equal(A.rotate_nearest(img, A.rotate_matrix(90.0, 16, 16)), np.rot90(img, 1, axes=(-2, -1)))
+    assert np.array_equal(A.rotate_nearest(img, A.rotate_matrix(-90.0, 16, 16)), np.rot90(img, -1, axes=(-2, -1)))
+    # sector equivariance on an annulus, centroid at the rotation centre
+    H = W = 128
+    r, c = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    rad = np.hypot(r - 63.5, c - 63.5)
+    ring = ((rad > 20) & (rad < 40)).astype(np.float32)
+    ids0 = oracle.sector_map(torch.from_numpy(ring)[None], 126)[0].numpy()
+    for n in (1, 5, 31):
+        m = A.rotate_matrix(A.rotation_angle_degree(n), H, W)
+        moved = A.rotate_nearest(ids0.astype(np.float32) + 1.0, m) - 1.0      # carry the ids with the pixels
+        sel = (moved >= 0) & (ring > 0) & (A.rotate_nearest(ring, m) > 0)
+        ids_new = oracle.sector_map(torch.from_numpy(A.rotate_nearest(ring, m))[None], 126)[0].numpy()
+        d = (ids_new[sel] - moved[sel]) % 126
+        # nearest-neighbour resampling moves a pixel by up to half a pixel: ids within one sector of the exact shift
+        assert np.all((d == n % 126) | (d == (n - 1) % 126) | (d == (n + 1) % 126))
+        assert np.mean(d == n % 126) > 0.8
