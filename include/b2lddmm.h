@@ -216,6 +216,13 @@ int b2_augment_volume(const float* vol, float* out, const double* xform, const i
  * (affine.py:74,78); S (B,R,C), n (B) int32 on the device. */
 int b2_roll_rows(const float* S, float* out, const int32_t* n, int64_t B, int64_t R, int64_t C, void* stream);
 
+/* ---- slice regrouping behind the path (joint_registration_regression_trainer.py:54-120) ----
+ * u (P,C,H,W) per-pair fields; pair_slot (P) int32 on the device: slice*F + frame position of pair p, or -1 for a
+ * pair beyond the F frames kept.  out (n_slices,C,F,H,W): frames cropped to F, missing frames zero (the call
+ * zero-fills out first). */
+int b2_regroup_pairs(const float* u, const int32_t* pair_slot, float* out, int64_t P, int64_t n_slices,
+                     int64_t F, int64_t C, int64_t H, int64_t W, void* stream);
+
 /* Device properties the host side needs for grid sizing / reporting. */
 int b2_device_sm_count(int device);
 

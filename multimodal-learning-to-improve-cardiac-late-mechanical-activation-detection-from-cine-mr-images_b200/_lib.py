@@ -73,6 +73,7 @@ SIGNATURES = {
                                   c_int, c_int, c_f]),
     "b2_augment_volume": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f]),
     "b2_roll_rows": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_f]),
+    "b2_regroup_pairs": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f]),
     "b2_device_sm_count": (c_int, [c_int]),
 }
 

@@ -3,12 +3,17 @@
 * ``split_vol_to_registration_pairs``  behaviour of /root/reference/modules/data/__init__.py:93-121
 * ``align_n_frames_to``                behaviour of /root/reference/modules/data/datareader/DENSE_IO_utils.py:2-46
 
-Same names, arguments and error behaviour, written independently; both are checked against the reference's own
-code through the committed golden vectors (tests/golden/ref_boundary.npz).
+* ``merge_data_of_same_slice_from_batch``  behaviour of
+  /root/reference/modules/trainer/joint_registration_regression_trainer.py:54-120, with the displacement
+  regrouping done by one device kernel (``b2_regroup_pairs``) instead of per-slice stack / permute / pad.
+
+Same names, arguments and error behaviour, written independently; all are checked against the reference's own
+code through the committed golden vectors (tests/golden/ref_boundary.npz, ref_regroup.npz).
 """
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 _SPLITS = ("Lagrangian", "Eulerian")
 
@@ -48,3 +53,44 @@ def align_n_frames_to(volume, n_target_frames, frame_idx=-1, padding_method="edg
         return volume[(slice(None),) * axis + (slice(0, n_target_frames),)]
     widths = [(0, n_target_frames - have) if ax == axis else (0, 0) for ax in range(volume.ndim)]
     return np.pad(volume, widths, mode=padding_method)
+
+
+def merge_data_of_same_slice_from_batch(batch, reg_pred_dict, n_frames_to_use_for_regression, used_device):
+    """Regroup the per-pair outputs of a batch by slice.
+
+    ``batch['slice_full_id']`` names the slice of every pair; the displacement fields (P,2,H,W) of a slice are laid
+    out in batch order as frames of a (2, F, H, W) block, cropped to ``F = n_frames_to_use_for_regression`` or
+    zero-padded at the end; ``TOS`` / ``sector_LMA_labels`` / ``slice_LMA_label`` are taken from the first pair of
+    each slice.  Returns the reference's dict.  Slices are ordered by first appearance (the reference iterates a
+    ``set``, i.e. in arbitrary order; ``'batch_slice_full_ids'`` names the order used).
+    """
+    from . import _lib
+    from ._lib import check, lib, ptr, require_cuda, stream
+    ids = list(batch["slice_full_id"])
+    u = reg_pred_dict["displacement"].contiguous()
+    require_cuda(u)
+    P, C, H, W = u.shape
+    if len(ids) != P:
+        raise _lib.B2Error(f"{len(ids)} slice ids for {P} pairs")
+    F = int(n_frames_to_use_for_regression)
+    order, seen, first, slot = [], {}, [], []
+    for p, sid in enumerate(ids):
+        if sid not in seen:
+            seen[sid] = [len(order), 0]
+            order.append(sid)
+            first.append(p)
+        s, pos = seen[sid]
+        slot.append(s * F + pos if pos < F else -1)
+        seen[sid][1] = pos + 1
+    slot_d = torch.tensor(slot, dtype=torch.int32).to(u.device)
+    out = torch.empty((len(order), C, F, H, W), dtype=u.dtype, device=u.device)
+    check(lib().b2_regroup_pairs(ptr(u), ptr(slot_d), ptr(out), P, len(order), F, C, H, W, stream()), "b2_regroup_pairs")
+    _lib.count_launch()
+    first_t = torch.tensor(first)
+    return {
+        "pred_displacement_fields": out,
+        "TOS": batch["TOS"][first_t].to(used_device),
+        "sector_LMA_labels": batch["sector_LMA_labels"][first_t].to(used_device),
+        "slice_LMA_label": torch.tensor([batch["slice_LMA_label"][i].item() for i in first]).to(used_device),
+        "batch_slice_full_ids": order,
+    }

@@ -99,3 +99,28 @@ def registration_reconstruction_loss(pred, target, sigma=0.03, regularization_we
     recon = torch.mean((tar - Sdef) ** 2)
     reg = (pred["velocity"] * pred["momentum"]).sum() / tar.numel()
     return 0.5 * recon / (sigma * sigma) + reg * regularization_weight
+
+
+def merge_data_of_same_slice_from_batch(batch, reg_pred_dict, n_frames_to_use_for_regression):
+    """Slice regrouping, behaviour of /root/reference/modules/trainer/joint_registration_regression_trainer.py:54-120
+    (golden-checked): per slice, the displacement fields of its pairs in batch order -> (2, F, H, W), cropped or
+    zero-padded to F frames; labels from the slice's first pair.  Slices in order of first appearance."""
+    ids = list(batch["slice_full_id"])
+    order = list(dict.fromkeys(ids))
+    F = int(n_frames_to_use_for_regression)
+    fields, first = [], []
+    for sid in order:
+        idx = [i for i, x in enumerate(ids) if x == sid]
+        first.append(idx[0])
+        d = torch.stack([reg_pred_dict["displacement"][i] for i in idx], dim=1)[:, :F]      # (2, n, H, W)
+        if d.shape[1] < F:
+            d = torch.cat([d, d.new_zeros(d.shape[0], F - d.shape[1], *d.shape[2:])], dim=1)
+        fields.append(d)
+    ft = torch.tensor(first)
+    return {
+        "pred_displacement_fields": torch.stack(fields, dim=0),
+        "TOS": batch["TOS"][ft],
+        "sector_LMA_labels": batch["sector_LMA_labels"][ft],
+        "slice_LMA_label": torch.tensor([batch["slice_LMA_label"][i].item() for i in first]),
+        "batch_slice_full_ids": order,
+    }

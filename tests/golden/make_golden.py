@@ -21,7 +21,10 @@ are for the callers either side of it:
 * ``translate`` / ``rotate``           /root/reference/modules/data/augmentation/affine.py:24-87
   (numpy parts as is; the skimage call is recorded through a stub: angle and keyword arguments).
 
-Outputs ``tests/golden/ref_boundary.npz`` and ``tests/golden/ref_augment.npz`` (committed).
+* ``merge_data_of_same_slice_from_batch``
+                                       /root/reference/modules/trainer/joint_registration_regression_trainer.py:54-120
+
+Outputs ``tests/golden/ref_boundary.npz``, ``ref_augment.npz`` and ``ref_regroup.npz`` (committed).
 """
 import importlib.util
 import json
@@ -35,6 +38,7 @@ import torch
 REF = pathlib.Path("/root/reference")
 OUT = pathlib.Path(__file__).resolve().parent / "ref_boundary.npz"
 OUT_AUG = pathlib.Path(__file__).resolve().parent / "ref_augment.npz"
+OUT_REGROUP = pathlib.Path(__file__).resolve().parent / "ref_regroup.npz"
 SKROTATE_CALLS = []
 
 
@@ -120,6 +124,45 @@ def main():
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes, {len(out)} arrays)")
     make_augment_golden()
+    make_regroup_golden()
+
+
+def make_regroup_golden():
+    """merge_data_of_same_slice_from_batch of joint_registration_regression_trainer.py:54-120.
+
+    The trainer module imports lagomorph / wandb / tensorboard at the top and cannot be imported here, so the
+    function definition alone is compiled from the reference file (read in place, nothing copied) and run."""
+    import ast
+    path = REF / "modules/trainer/joint_registration_regression_trainer.py"
+    tree = ast.parse(path.read_text())
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "merge_data_of_same_slice_from_batch")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), str(path), "exec"), ns)
+    merge = ns["merge_data_of_same_slice_from_batch"]
+    g = torch.Generator().manual_seed(2434)
+    ids = ["p1_s0", "p1_s1", "p1_s0", "p2_s0", "p1_s1", "p1_s0", "p1_s0", "p2_s0", "p1_s0"]     # 5 / 2 / 2 pairs
+    P, H, W = len(ids), 6, 5
+    uniq = list(dict.fromkeys(ids))
+    tos_per = {k: torch.rand(126, generator=g) * 60 for k in uniq}
+    lab_per = {k: (torch.rand(126, generator=g) > 0.5).long() for k in uniq}
+    batch = {
+        "slice_full_id": ids,
+        "TOS": torch.stack([tos_per[k] for k in ids]),
+        "sector_LMA_labels": torch.stack([lab_per[k] for k in ids]),
+        "slice_LMA_label": torch.tensor([uniq.index(k) % 2 for k in ids]),
+    }
+    pred = {"displacement": torch.randn(P, 2, H, W, generator=g)}
+    out = {"ids": np.array(ids), "displacement": pred["displacement"].numpy(), "TOS": batch["TOS"].numpy(),
+           "sector_LMA_labels": batch["sector_LMA_labels"].numpy(), "slice_LMA_label": batch["slice_LMA_label"].numpy()}
+    for F in (3, 4, 7):
+        r = merge(batch, pred, F, torch.device("cpu"))
+        out[f"F{F}_ids"] = np.array(r["batch_slice_full_ids"])
+        out[f"F{F}_fields"] = r["pred_displacement_fields"].numpy()
+        out[f"F{F}_TOS"] = r["TOS"].numpy()
+        out[f"F{F}_labels"] = r["sector_LMA_labels"].numpy()
+        out[f"F{F}_slice_label"] = r["slice_LMA_label"].numpy()
+    np.savez_compressed(OUT_REGROUP, **out)
+    print(f"wrote {OUT_REGROUP} ({OUT_REGROUP.stat().st_size} bytes, {len(out)} arrays)")
 
 
 def make_augment_golden():

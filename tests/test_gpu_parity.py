@@ -540,6 +540,36 @@ def test_augmented_batch_through_the_path(pkg, dev):
     assert relerr(b["strain_matrix"], rolled) < 1e-3, f"{relerr(b['strain_matrix'], rolled):.2e}"
 
 
+@pytest.mark.parametrize("F", [3, 4, 7])
+def test_regroup_pairs_matches_reference_golden(pkg, dev, F):
+    """Device slice regrouping vs the output of the reference's own merge_data_of_same_slice_from_batch."""
+    import pathlib
+    from test_oracle_cpu import check_regroup_against_golden
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_regroup.npz")
+
+    def merge(batch, pred, F):
+        return pkg.data.merge_data_of_same_slice_from_batch(batch, {"displacement": pred["displacement"].to(dev)}, F, dev)
+    check_regroup_against_golden(g, merge, F)
+
+
+@pytest.mark.parametrize("hw", [(128, 128), (33, 47)])
+def test_regroup_pairs_vs_oracle(pkg, oracle, dev, hw):
+    """Ragged batch (slices with 1..T pairs, interleaved), vectorised and scalar copy paths: bit-exact."""
+    H, W = hw
+    rng = np.random.default_rng(5)
+    ids = [f"s{int(k)}" for k in rng.integers(0, 6, 40)]
+    P = len(ids)
+    batch = {"slice_full_id": ids, "TOS": torch.rand(P, 126), "sector_LMA_labels": torch.randint(0, 2, (P, 126)),
+             "slice_LMA_label": torch.randint(0, 2, (P,))}
+    u = _rand(P, 2, H, W, seed=6)
+    for F in (2, 9, 48):
+        want = oracle.path.merge_data_of_same_slice_from_batch(batch, {"displacement": u}, F)
+        got = pkg.data.merge_data_of_same_slice_from_batch(batch, {"displacement": u.to(dev)}, F, dev)
+        assert got["batch_slice_full_ids"] == want["batch_slice_full_ids"]
+        assert torch.equal(got["pred_displacement_fields"].cpu(), want["pred_displacement_fields"])
+        assert torch.equal(got["TOS"].cpu(), want["TOS"]) and torch.equal(got["slice_LMA_label"].cpu(), want["slice_LMA_label"])
+
+
 def test_models_forward_volume_on_gpu(pkg, dev):
     """models shim end to end: forward_volume -> LMA net -> backward, keys/shapes of the trainer contract."""
     torch.manual_seed(2434)

@@ -350,3 +350,32 @@ def test_augment_rotation_properties(oracle, pkg):
         # nearest-neighbour resampling moves a pixel by up to half a pixel: ids within one sector of the exact shift
         assert np.all((d == n % 126) | (d == (n - 1) % 126) | (d == (n + 1) % 126))
         assert np.mean(d == n % 126) > 0.8
+
+
+# ----------------------------------------------------------------- slice regrouping (reference trainer helper)
+def _regroup_inputs(g):
+    batch = {"slice_full_id": [str(x) for x in g["ids"]], "TOS": torch.from_numpy(g["TOS"]),
+             "sector_LMA_labels": torch.from_numpy(g["sector_LMA_labels"]),
+             "slice_LMA_label": torch.from_numpy(g["slice_LMA_label"])}
+    return batch, {"displacement": torch.from_numpy(g["displacement"])}
+
+
+def check_regroup_against_golden(g, merge, F):
+    """Compare per slice id: the reference iterates a set, so its slice order is arbitrary."""
+    batch, pred = _regroup_inputs(g)
+    r = merge(batch, pred, F)
+    ref_ids = [str(x) for x in g[f"F{F}_ids"]]
+    assert sorted(r["batch_slice_full_ids"]) == sorted(ref_ids)
+    for j, sid in enumerate(r["batch_slice_full_ids"]):
+        k = ref_ids.index(sid)
+        assert np.array_equal(r["pred_displacement_fields"][j].cpu().numpy(), g[f"F{F}_fields"][k]), (F, sid)
+        assert np.array_equal(r["TOS"][j].cpu().numpy(), g[f"F{F}_TOS"][k])
+        assert np.array_equal(r["sector_LMA_labels"][j].cpu().numpy(), g[f"F{F}_labels"][k])
+        assert int(r["slice_LMA_label"][j]) == int(g[f"F{F}_slice_label"][k])
+
+
+@pytest.mark.parametrize("F", [3, 4, 7])
+def test_regroup_matches_reference(oracle, F):
+    import pathlib
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_regroup.npz")
+    check_regroup_against_golden(g, oracle.path.merge_data_of_same_slice_from_batch, F)
