@@ -78,7 +78,7 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
     if ws is None or ws.numel() < nbytes:
         ws = _workspace(nbytes, dev)
     check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), nbytes, stream()), "b2_shoot_fwd")
-    fused = H == W and H in (16, 32, 64, 128, 256)   # one persistent kernel (256: one 4-CTA cluster per pair)
+    fused = _fused_size(H, W)                        # one persistent kernel (256: one 4-CTA cluster per pair)
     _lib.count_launch(1 if fused else 3 + 3 * int(num_steps) + 2)   # path B: flat, 3 kernels per step, warp, strain
     return out
 
@@ -238,7 +238,10 @@ class ShootWarpStrainFunction(torch.autograd.Function):
 
 
 def _fused_size(H, W):
-    return H == W and H in (16, 32, 64, 128)
+    """Sizes served by a persistent fused kernel (they read strided cine volumes in place): one CTA per pair up to
+    128x128, one 4-CTA cluster per pair at 256x256 (unless B2_NO_CLUSTER selects the op-level path)."""
+    import os
+    return H == W and (H in (16, 32, 64, 128) or (H == 256 and not os.environ.get("B2_NO_CLUSTER")))
 
 
 def _rows_dense(t):

@@ -570,6 +570,46 @@ def test_regroup_pairs_vs_oracle(pkg, oracle, dev, hw):
         assert torch.equal(got["TOS"].cpu(), want["TOS"]) and torch.equal(got["slice_LMA_label"].cpu(), want["slice_LMA_label"])
 
 
+def test_new_entry_points_reject_bad_arguments(pkg, dev):
+    """Argument errors of the loss-epilogue / augmentation / regrouping entries come back as B2_E_* codes."""
+    L = pkg._lib
+    lib, ptr, st = L.lib(), L.ptr, L.stream()
+    x = torch.zeros(2, 2, 16, 16, device=dev)
+    t2 = torch.zeros(2, 2, device=dev)
+    assert lib.b2_recon_loss_terms(None, None, None, None, None, 2, 16, 16, st) == -1            # NULL output
+    assert lib.b2_recon_loss_terms(ptr(x), None, None, None, ptr(t2), 2, 16, 16, st) == -1       # sdef without tar
+    assert lib.b2_recon_loss_terms(None, None, None, None, ptr(t2), 0, 16, 16, st) == -2         # shape
+    assert lib.b2_warp_sqerr_bwd(None, ptr(x), ptr(x), ptr(x), ptr(x), None, 2, 1, 16, 16, 0, 0, 0, 0, 0, st) == -1
+    assert lib.b2_warp_sqerr_bwd(ptr(t2), ptr(x), ptr(x), ptr(x), ptr(x), None, 2, 1, 16, 16, 0, 0, 0, 7, 0, st) == -5
+    assert lib.b2_augment_volume(ptr(x), ptr(x), ptr(x), None, 1, 1, 16, 16, st) == -5           # in place
+    assert lib.b2_roll_rows(ptr(x), None, ptr(x), 1, 4, 4, st) == -1
+    assert lib.b2_regroup_pairs(ptr(x), ptr(x), ptr(x), 2, 0, 4, 2, 16, 16, st) == -2
+    with pytest.raises(RuntimeError):
+        pkg.augment.rotate_translate_volume(torch.zeros(2, 2, 3, 8, 8, device=dev), 1)
+    with pytest.raises(RuntimeError):
+        pkg.augment.rotate_translate_volume(torch.zeros(2, 1, 3, 8, 8, device=dev), [1, 2, 3])
+    with pytest.raises(RuntimeError):
+        pkg.augment.roll_rows(torch.zeros(2, 126), 1)                                            # CPU tensor
+    # loss_terms on the op-level path needs the sdef and vel outputs (B2_E_NULL), and src/tar everywhere
+    m = pkg.FluidMetric(PARAMS)
+    v0 = torch.zeros(2, 2, 64, 128, device=dev)
+    with pytest.raises(RuntimeError):
+        pkg.shooting._launch_shoot(v0, None, None, None, None, m, 2, 1.0, 0, 3, 1, 2, 1, {"loss_terms": True}, False,
+                                   False, False)
+
+
+def test_cluster_path_reads_cine_volume_in_place(pkg, dev):
+    """256x256: strided views of one cine volume (no pair construction) give the same bits as dense copies."""
+    B, T, H, W, S = 2, 3, 256, 256, 2
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).to(dev)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 61, 3.0).to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    m = pkg.FluidMetric(PARAMS)
+    a = pkg.shoot_warp_strain(v0, sv, tv, m, num_steps=S, loss_terms=True)
+    b = pkg.shoot_warp_strain(v0, sv.contiguous(), tv.contiguous(), m, num_steps=S, loss_terms=True)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
 def test_models_forward_volume_on_gpu(pkg, dev):
     """models shim end to end: forward_volume -> LMA net -> backward, keys/shapes of the trainer contract."""
     torch.manual_seed(2434)
