@@ -462,7 +462,7 @@ def test_expmap_momentum_regulariser_gradient(pkg, oracle, dev):
     u = oracle.expmap(mc, mr, num_steps=S)
     ((u * gu).sum() + (g_reg.view(P, 1, 1, 1) * mc.sharp(mr) * mr).sum()).backward()
     L = pkg._lib
-    md = m0.to(dev)
+    md, gud, grd = m0.to(dev), gu.to(dev), g_reg.to(dev)       # keep the device copies alive across the calls
     out = pkg.shooting._launch_shoot(md, None, None, None, None, pkg.FluidMetric(PARAMS), S, 1.0, 0, 3, 1, P, 1, {}, True,
                                      False, True)
     for oplevel in (False, True):
@@ -473,7 +473,7 @@ def test_expmap_momentum_regulariser_gradient(pkg, oracle, dev):
         if oplevel:
             os.environ["B2_BWD_OPLEVEL"] = "1"
         try:
-            L.check(L.lib().b2_shoot_bwd_loss(L.ptr(gu.to(dev)), None, None, L.ptr(g_reg.to(dev)), L.ptr(md),
+            L.check(L.lib().b2_shoot_bwd_loss(L.ptr(gud), None, None, L.ptr(grd), L.ptr(md),
                                               L.ptr(out["traj"]), L.ptr(gm), P, H, W, S, *PARAMS, 1.0, 0, 1, L.ptr(ws),
                                               nbytes, L.stream()))
         finally:
