@@ -191,7 +191,8 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         if with_strain and gS is not None:
             du = torch.empty_like(u)
             tar_c = tar.reshape(B, T1, H, W).contiguous()
-            check(lib().b2_strain_sector_bwd(ptr(gS.contiguous()), ptr(u), ptr(tar_c), ptr(moments), ptr(table),
+            gS_c = gS.contiguous()          # named: a temporary would be freed before the launch is enqueued
+            check(lib().b2_strain_sector_bwd(ptr(gS_c), ptr(u), ptr(tar_c), ptr(moments), ptr(table),
                                              ptr(counts), ptr(du), B, T1, H, W, n_sectors, n_frames, stream()),
                   "b2_strain_sector_bwd")
             _lib.count_launch()
@@ -216,11 +217,12 @@ class ShootWarpStrainFunction(torch.autograd.Function):
             src_c = src.reshape(P, 1, H, W).contiguous() if src_per_pair else src.contiguous()
             du = torch.empty_like(u)
             d1 = torch.empty_like(src_c) if want_dsrc else None
+            gsdef_c = gsdef.contiguous()
             if src_per_pair:
-                check(lib().b2_interp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(d1), ptr(du), P, P, P, 1,
+                check(lib().b2_interp_bwd(ptr(gsdef_c), ptr(src_c), ptr(u), ptr(d1), ptr(du), P, P, P, 1,
                                           H, W, 1.0, background, stream()), "b2_interp_bwd")
             else:
-                check(lib().b2_warp_bwd(ptr(gsdef.contiguous()), ptr(src_c), ptr(u), ptr(d1), ptr(du), B, T1, 1,
+                check(lib().b2_warp_bwd(ptr(gsdef_c), ptr(src_c), ptr(u), ptr(d1), ptr(du), B, T1, 1,
                                         H, W, 1.0, background, stream()), "b2_warp_bwd")
             _lib.count_launch()
             gu_tot = add(gu_tot, du)

@@ -77,7 +77,8 @@ class StrainMatrixFunction(torch.autograd.Function):
         u, tar, moments, table, counts = ctx.saved_tensors
         B, T1, _, H, W = u.shape
         du = torch.empty_like(u)
-        check(lib().b2_strain_sector_bwd(ptr(gS.contiguous()), ptr(u), ptr(tar), ptr(moments), ptr(table),
+        gS_c = gS.contiguous()
+        check(lib().b2_strain_sector_bwd(ptr(gS_c), ptr(u), ptr(tar), ptr(moments), ptr(table),
                                          ptr(counts), ptr(du), B, T1, H, W, *ctx.dims, stream()),
               "b2_strain_sector_bwd")
         _lib.count_launch()
