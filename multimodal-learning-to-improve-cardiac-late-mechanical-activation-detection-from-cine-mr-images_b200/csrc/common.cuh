@@ -84,6 +84,26 @@ __device__ __forceinline__ Taps make_taps(float p0, float p1, int H, int W) {
   return t;
 }
 
+// Same taps for the forward gathers.  Under the clamp rule i0 = clamp(floor, 0, H-1), i1 = clamp(floor + 1, 0, H-1):
+// clamping floor to [-1, H-1] in float first (NaN -> -1) gives the same two indices with one max and one add+min
+// per axis - 5 instructions fewer per gather, bit-identical results.  (The adjoint kernels keep make_taps: there
+// the shorter form costs more in register spills than it saves.)
+template <int BG>
+__device__ __forceinline__ Taps make_taps_fwd(float p0, float p1, int H, int W) {
+  if (BG == B2_BG_ZERO) return make_taps<BG>(p0, p1, H, W);
+  Taps t;
+  const float f0 = floorf(p0), f1 = floorf(p1);
+  t.a = p0 - f0;
+  t.b = p1 - f1;
+  t.m00 = t.m10 = t.m01 = t.m11 = 1.f;
+  const int ig = (int)fminf(fmaxf(f0, -1.0f), (float)(H - 1));
+  const int jg = (int)fminf(fmaxf(f1, -1.0f), (float)(W - 1));
+  const int i0 = max(ig, 0), i1 = min(ig + 1, H - 1);
+  const int j0 = max(jg, 0), j1 = min(jg + 1, W - 1);
+  t.o00 = i0 * W + j0; t.o10 = i1 * W + j0; t.o01 = i0 * W + j1; t.o11 = i1 * W + j1;
+  return t;
+}
+
 template <int BG>
 __device__ __forceinline__ float tap_sample(const Taps& t, float v00, float v10, float v01, float v11) {
   float oma = 1.f - t.a, omb = 1.f - t.b;
@@ -119,7 +139,7 @@ __device__ __forceinline__ void gather2(const float* f, int plane, float p0, flo
     q += plane;
     w1 = ((c00 * q[0] + c01 * q[1]) + c10 * q[W]) + c11 * q[W + 1];
   } else {
-    const Taps t = make_taps<BG>(p0, p1, H, W);
+    const Taps t = make_taps_fwd<BG>(p0, p1, H, W);
     w0 = tap_sample<BG>(t, f[t.o00], f[t.o10], f[t.o01], f[t.o11]);
     f += plane;
     w1 = tap_sample<BG>(t, f[t.o00], f[t.o10], f[t.o01], f[t.o11]);
@@ -136,7 +156,7 @@ __device__ __forceinline__ float gather1_ldg(const float* __restrict__ f, float 
     const float* q = f + i0 * W + j0;
     return (((oma * omb) * __ldg(q) + (oma * b) * __ldg(q + 1)) + (a * omb) * __ldg(q + W)) + (a * b) * __ldg(q + W + 1);
   }
-  const Taps t = make_taps<BG>(p0, p1, H, W);
+  const Taps t = make_taps_fwd<BG>(p0, p1, H, W);
   return tap_sample<BG>(t, __ldg(f + t.o00), __ldg(f + t.o10), __ldg(f + t.o01), __ldg(f + t.o11));
 }
 

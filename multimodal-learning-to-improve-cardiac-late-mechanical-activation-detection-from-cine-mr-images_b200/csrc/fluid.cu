@@ -233,7 +233,7 @@ adstar_rows_kernel(const float* __restrict__ u, const float* __restrict__ m0, fl
     const float sr = (r == 0 || r == H - 1) ? 1.f : 0.5f, sc = (c == 0 || c == W - 1) ? 1.f : 0.5f;
     const float d00 = sr * (dn.x - up.x), d10 = sr * (dn.y - up.y);
     const float d01 = sc * (rt.x - lf.x), d11 = sc * (rt.y - lf.y);
-    const Taps t = make_taps<BG>((float)r + ce.x, (float)c + ce.y, H, W);
+    const Taps t = make_taps_fwd<BG>((float)r + ce.x, (float)c + ce.y, H, W);
     const float w0 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
     const float w1 = tap_sample<BG>(t, mp[N + t.o00], mp[N + t.o10], mp[N + t.o01], mp[N + t.o11]);
     z[rr * LD + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
@@ -267,7 +267,7 @@ compose_rows_kernel(const float2* __restrict__ zg, const float* __restrict__ u, 
     const float2 v = z[rr * LD + c];
     float a = mdt * v.x, b = mdt * v.y;
     if (u0) {
-      const Taps t = make_taps<BG>((float)r + a, (float)c + b, H, W);
+      const Taps t = make_taps_fwd<BG>((float)r + a, (float)c + b, H, W);
       a += tap_sample<BG>(t, u0[t.o00], u0[t.o10], u0[t.o01], u0[t.o11]);
       b += tap_sample<BG>(t, u0[N + t.o00], u0[N + t.o10], u0[N + t.o01], u0[N + t.o11]);
     }

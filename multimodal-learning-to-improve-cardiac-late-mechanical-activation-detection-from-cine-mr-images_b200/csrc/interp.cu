@@ -42,7 +42,7 @@ interp_fwd_kernel(const float* __restrict__ I, const float* __restrict__ u, floa
   for (int p = blockIdx.y; p < P; p += gridDim.y) {
     const float* up = u + (size_t)(p * su) * 2 * N + x;
     const float u0 = up[0], u1 = up[N];
-    const Taps t = make_taps<BG>((float)r + dt * u0, (float)c + dt * u1, H, W);
+    const Taps t = make_taps_fwd<BG>((float)r + dt * u0, (float)c + dt * u1, H, W);
     const float* Ic = I + (size_t)((p / gI) * sI) * nc * N;
     float* op = out + (size_t)p * nc * N + x;
 #pragma unroll

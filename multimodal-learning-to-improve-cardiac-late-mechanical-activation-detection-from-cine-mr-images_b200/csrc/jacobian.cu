@@ -139,7 +139,7 @@ adstar_fwd_kernel(const float* __restrict__ u, const float* __restrict__ m0, flo
     const float* mp = m0 + (size_t)p * 2 * N;
     const float d00 = sr * (u0[odn] - u0[oup]), d10 = sr * (u1[odn] - u1[oup]);
     const float d01 = sc * (u0[ort] - u0[olf]), d11 = sc * (u1[ort] - u1[olf]);
-    const Taps t = make_taps<BG>((float)r + u0[x], (float)c + u1[x], H, W);
+    const Taps t = make_taps_fwd<BG>((float)r + u0[x], (float)c + u1[x], H, W);
     const float w0 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
     mp += N;
     const float w1 = tap_sample<BG>(t, mp[t.o00], mp[t.o10], mp[t.o01], mp[t.o11]);
