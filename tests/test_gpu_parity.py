@@ -407,7 +407,8 @@ def test_loss_epilogue_terms(pkg, oracle, dev, cfg):
     assert abs(fused.item() - float(lc)) < max(1e-5, 3 * own) * abs(float(lc))
 
 
-@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 4, "Lagrangian"), (2, 3, 64, 64, 3, "Eulerian"), (1, 3, 64, 128, 2, "Lagrangian")])
+@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 4, "Lagrangian"), (2, 3, 64, 64, 3, "Eulerian"), (1, 3, 64, 128, 2, "Lagrangian"),
+                                 (1, 2, 256, 256, 2, "Lagrangian")])
 def test_loss_epilogue_backward(pkg, oracle, dev, cfg):
     """Gradient of the reference's training loss taken through the fused loss terms (b2_warp_sqerr_bwd + the
     closed-form regularisation gradient in b2_shoot_bwd_loss) vs autograd through the oracle, and vs the unfused
