@@ -632,9 +632,11 @@ def test_models_forward_volume_on_gpu(pkg, dev):
     assert set(pair) >= {"displacement", "velocity", "momentum", "deformed_source"}
 
 
-def test_host_pipeline_matches_resident(pkg, dev):
-    """Host-buffer entry point (chunked H2D/compute overlap, strided cine volume) == resident call, bit for bit."""
-    B, T, H, W, S = 5, 4, 64, 64, 4
+@pytest.mark.parametrize("cfg", [(5, 4, 64, 64, 4), (3, 3, 256, 256, 2)])
+def test_host_pipeline_matches_resident(pkg, dev, cfg):
+    """Host-buffer entry point (chunked H2D/compute overlap, strided cine volume) == resident call, bit for bit
+    (single-CTA kernel at 64x64, 4-CTA cluster kernel at 256x256)."""
+    B, T, H, W, S = cfg
     vol = pkg.synthetic.synthetic_masks(B, T, H, W).pin_memory()
     v0 = _smooth_v0(pkg, B * (T - 1), H, W, 29, 2.5).pin_memory()
     metric = pkg.FluidMetric(PARAMS)
