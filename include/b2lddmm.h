@@ -223,6 +223,14 @@ int b2_roll_rows(const float* S, float* out, const int32_t* n, int64_t B, int64_
 int b2_regroup_pairs(const float* u, const int32_t* pair_slot, float* out, int64_t P, int64_t n_slices,
                      int64_t F, int64_t C, int64_t H, int64_t W, void* stream);
 
+/* ---- binary masks over PCIe as one byte per pixel (host-buffer entry point) ----
+ * The reference's cine inputs are fp32 volumes holding exactly 0 or 1 (README.md:21, joint_dataset.py:61-89).
+ * b2_pack_binary_u8_host runs on the HOST (multi-threaded): dst[i] = (uint8_t)src[i]; returns 1 if every value was
+ * exactly 0.0f or 1.0f, 0 otherwise (the caller must then copy the fp32 data), < 0 on bad arguments.
+ * b2_unpack_u8 widens on the device: out[i] = (float)in[i]; n multiple of 4, in 4-byte / out 16-byte aligned. */
+int b2_pack_binary_u8_host(const float* src_host, uint8_t* dst_host, int64_t n, int threads);
+int b2_unpack_u8(const uint8_t* in, float* out, int64_t n, void* stream);
+
 /* Device properties the host side needs for grid sizing / reporting. */
 int b2_device_sm_count(int device);
 

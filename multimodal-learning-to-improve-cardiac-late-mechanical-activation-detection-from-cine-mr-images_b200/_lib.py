@@ -74,6 +74,8 @@ SIGNATURES = {
     "b2_augment_volume": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f]),
     "b2_roll_rows": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_f]),
     "b2_regroup_pairs": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f]),
+    "b2_pack_binary_u8_host": (c_int, [c_f, c_f, c_i64, c_int]),
+    "b2_unpack_u8": (c_int, [c_f, c_f, c_i64, c_f]),
     "b2_device_sm_count": (c_int, [c_int]),
 }
 

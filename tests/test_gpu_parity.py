@@ -658,6 +658,45 @@ def test_host_pipeline_matches_resident(pkg, dev, cfg):
     assert torch.equal(S2, ref["strain_matrix"].cpu())
 
 
+def test_host_pipeline_mask_packing(pkg, dev):
+    """Binary masks cross PCIe as u8 (verified on the host) - same bits as the fp32 copy; a non-binary chunk falls
+    back to fp32 and still matches the resident call."""
+    B, T, H, W, S = 4, 3, 64, 64, 3
+    metric = pkg.FluidMetric(PARAMS)
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).pin_memory()
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 71, 2.5).pin_memory()
+    packed = pkg.HostPipeline(B, T, H, W, metric, num_steps=S, chunk_slices=2, device=dev, pack_masks=True)
+    plain = pkg.HostPipeline(B, T, H, W, metric, num_steps=S, chunk_slices=2, device=dev, pack_masks=False)
+    a = packed(v0, vol).clone()
+    b = plain(v0, vol).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
+        assert torch.equal(packed.result()[k], plain.result()[k]), k
+    n_mask, n_v0 = vol.numel(), v0.numel() * 4
+    assert packed.h2d_bytes == n_v0 + n_mask and plain.h2d_bytes == n_v0 + 4 * n_mask
+    # grey-valued volume: slices 2-3 (second chunk) are not binary -> fp32 copy for that chunk only
+    grey = vol.clone()
+    grey[2:] *= 0.75
+    grey = grey.pin_memory()
+    c = packed(v0, grey).clone()
+    torch.cuda.synchronize()
+    assert packed.h2d_bytes == n_v0 + n_mask // 2 + 4 * (n_mask // 2)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(grey.to(dev), "Lagrangian", 3)
+    ref = pkg.shoot_warp_strain(v0.to(dev), sv, tv, metric, num_steps=S)
+    assert torch.equal(c, ref["strain_matrix"].cpu())
+    assert torch.equal(packed.result()["deformed_source"], ref["deformed_source"])
+    # host helper on its own: exactness check and values
+    L = pkg._lib
+    src = (torch.rand(4096) > 0.5).float()
+    dst = torch.empty(4096, dtype=torch.uint8)
+    assert L.lib().b2_pack_binary_u8_host(L.ptr(src), L.ptr(dst), 4096, 2) == 1 and torch.equal(dst.float(), src)
+    src[17] = 1.0000001
+    assert L.lib().b2_pack_binary_u8_host(L.ptr(src), L.ptr(dst), 4096, 2) == 0
+    src[17] = float("nan")
+    assert L.lib().b2_pack_binary_u8_host(L.ptr(src), L.ptr(dst), 4096, 0) == 0
+
+
 def test_full_size_properties(pkg, dev):
     """BASELINE config-2 size (P=1536, 128^2, S=10): size-independent properties instead of the oracle."""
     B, T, H, W, S = 64, 25, 128, 128, 10
