@@ -339,6 +339,14 @@ class HostPipeline:
         self.copy_stream = torch.cuda.Stream(self.dev)
         dev, T1, cs = self.dev, self.T1, self.chunk
         self.pack_masks = bool(pack_masks) and (T * H * W) % 4 == 0
+        if int(pack_threads) <= 0:    # CPUs this process may use, shared with the other ranks of the node
+            import os
+            try:
+                ncpu = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                ncpu = os.cpu_count() or 1
+            local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            pack_threads = max(1, min(16, ncpu // local_world))
         self.pack_threads = int(pack_threads)
         self.h2d_bytes = 0
         self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
