@@ -346,7 +346,14 @@ class HostPipeline:
             except (AttributeError, OSError):
                 ncpu = os.cpu_count() or 1
             local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            pack_threads = max(1, min(16, ncpu // local_world))
+            share = ncpu // local_world
+            pack_threads = max(1, min(16, share))
+            # The narrowing pass must stay hidden behind the v0 copy of the same chunk and must not fight the other
+            # ranks for cores.  Measured on the 8-GPU box (32 host CPUs): 1 or 2 ranks (>= 12 threads each) gain 25 %
+            # (5.6 -> 4.25-4.4 ms per step); 4 ranks with 8 threads each lose (6.9 vs 5.9-6.4 ms) and 8 ranks with 4
+            # threads lose (15.3 vs 13.3 ms), so ranks with fewer than 12 host threads copy fp32.
+            if share < 12:
+                self.pack_masks = False
         self.pack_threads = int(pack_threads)
         self.h2d_bytes = 0
         self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
