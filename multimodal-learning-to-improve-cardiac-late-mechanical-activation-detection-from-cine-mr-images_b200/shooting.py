@@ -316,7 +316,7 @@ class HostPipeline:
     """Host-buffer entry point of the hot path: pinned host inputs in, strain matrices on the host out.
 
     The batch is cut into chunks of whole slices; the H2D copy of chunk i+1 (copy stream) overlaps the
-    fused shooting kernel of chunk i (compute stream), with double-buffered device staging, so a step
+    fused shooting kernel of chunk i (compute stream), with triple-buffered device staging, so a step
     costs max(PCIe time, kernel time) instead of their sum.  Device outputs of the whole batch stay
     available in ``self.out`` (same keys as :func:`shoot_warp_strain`).  Inference only (no autograd).
 
@@ -356,9 +356,15 @@ class HostPipeline:
                 self.pack_masks = False
         self.pack_threads = int(pack_threads)
         self.h2d_bytes = 0
+        # Three staging buffers: with two, the copy of chunk i+1 has to wait for the kernel of chunk i-1, which ends
+        # just about when the copy of chunk i does (kernel and copy times per chunk are nearly equal) - any jitter
+        # stalls the copy engine.
+        self.n_stages = 3
+        self._next_stage = 0
         self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
                        "v0": torch.empty((cs * T1, 2, H, W), device=dev),
-                       "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False} for _ in range(2)]
+                       "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False}
+                      for _ in range(self.n_stages)]
         if self.pack_masks:
             for st in self.stage:
                 st["vol_u8"] = torch.empty(cs * T * H * W, dtype=torch.uint8, device=dev)
@@ -385,7 +391,8 @@ class HostPipeline:
             for i, b0 in enumerate(range(0, B, cs)):
                 b1 = min(b0 + cs, B)
                 nb = b1 - b0
-                st = self.stage[i % 2]
+                st = self.stage[self._next_stage]                        # rotates across calls as well
+                self._next_stage = (self._next_stage + 1) % self.n_stages
                 with torch.cuda.stream(self.copy_stream):
                     if st["used"]:                                       # last kernel that read this stage is done
                         self.copy_stream.wait_event(st["free"])          # (also across consecutive calls)
