@@ -14,8 +14,12 @@
 // Compulsory HBM traffic per pair drops from the op-level 700*N bytes to the
 // inputs + outputs (~44*N bytes).
 //
-// Path B (256x256 / rectangular): the same algorithm as a sequence of the
+// 256x256: one 4-CTA thread-block cluster per frame-pair (shoot_cluster.cu), same residency idea with 64-row slabs.
+//
+// Path B (rectangular grids, or 256x256 with B2_NO_CLUSTER=1): the same algorithm as a sequence of the
 // op-level kernels (HBM-bound per op).
+//
+// Backward: shoot_bwd_kernel (fused EPDiff adjoint, square grids up to 128x128) or the op-level sweep.
 #include <stdlib.h>
 
 #include "fft.cuh"
