@@ -4,8 +4,9 @@
 // CTA of a cluster (4 SMs).  Row FFTs run on the slab in shared memory; for the column pass the four CTAs exchange
 // data through a per-pair scratch that stays in L2: every CTA stores its slab, the cluster synchronises, and every
 // CTA loads a MIRROR-CLOSED group of 64 spectrum columns (4 blocks of 16 cells: {0,8,1,15}, {2,14,3,13}, ...), so
-// the k <-> -k coupling of the fluid multiplier stays inside one CTA.  m / v never reach HBM; u_s and m0 live in the
-// same per-pair L2 scratch (2.5 MiB per cluster, ~92 MiB for 37 clusters) and are re-read by the gathers.
+// the k <-> -k coupling of the fluid multiplier stays inside one CTA.  m / v never reach HBM; u_s and m0 live in a
+// per-cluster L2 scratch and are re-read by the gathers; the exchange buffer is the field u_{s+1} is about to be
+// written into, so a cluster keeps 1.5 MiB live (50 MiB for the 33 resident clusters).
 // Three cluster barriers per EPDiff step (after compose, after the row pass, after the column pass).
 #include <cooperative_groups.h>
 
@@ -25,12 +26,22 @@ __constant__ int c_group_block[4][4] = {{0, 8, 1, 15}, {2, 14, 3, 13}, {4, 12, 5
 
 struct ClusterParams {
   b2_shoot_args a;
-  float* scratch;        // per cluster: [Zs (complex, 2 fields) | u ping | u pong | m0] + bins
+  float* scratch;        // per cluster: [u ping | u pong | m0] + bins; the spectrum exchange reuses the next-u field
   int64_t P;
   int64_t cluster_stride;   // floats of scratch per cluster
 };
 
 __device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? (q < 2 ? q : 5 - q) : (q ^ 1); }
+
+// The spectrum exchange buffer Zs (one complex field) has no memory of its own: it lives in the 2-plane field that
+// the coming compose will overwrite with u_{s+1} (dead until then).  Row r of the spectrum is placed so that the rows
+// CTA X reads LAST (its own slab, second exchange) occupy exactly the bytes X itself writes in that compose - rows
+// 64X .. 64X+31 in X's part of plane 0, rows 64X+32 .. 64X+63 in X's part of plane 1 - so no CTA can overwrite
+// spectrum rows another CTA still has to read, and the cluster needs no extra barrier.  Index in float2 units.
+__device__ __forceinline__ int zs_row(int r) {
+  const int x = r >> 6, lr = r & 63;
+  return (lr < 32 ? 0 : kCN / 2 - 32 * kCW) + x * (32 * kCW) + lr * kCW;
+}
 
 // One fluid operator on the slab in z (row layout in, row layout out): row FFT -> spectrum exchange through the
 // per-cluster L2 scratch Zs -> column FFT of a mirror-closed column group -> multiplier -> inverse, same way back.
@@ -44,12 +55,12 @@ __device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2
   fft_lines<256, kSR, -1, kCNT, 1, kLDR>(z, tw, tid);
   for (int k = 0; k < NBc; ++k) {                   // slab -> L2 scratch (cell order along c)
     const int lr = k * RBc + br;
-    Zs[(size_t)(r0 + lr) * W + c] = z[lr * kLDR + c];
+    Zs[zs_row(r0 + lr) + c] = z[lr * kLDR + c];
   }
   cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
   for (int i = tid; i < H * kSR; i += kCNT) {       // mirror-closed column group, all 256 rows
     const int r = i / kSR;
-    z[r * kLDC + lc] = Zs[(size_t)r * W + pc];
+    z[r * kLDC + lc] = Zs[zs_row(r) + pc];
   }
   __syncthreads();
   fft_lines<256, kSR, -1, kCNT, kLDC, 1>(z, tw, tid);
@@ -83,12 +94,12 @@ __device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2
   fft_lines<256, kSR, +1, kCNT, kLDC, 1>(z, tw, tid);
   for (int i = tid; i < H * kSR; i += kCNT) {
     const int r = i / kSR;
-    Zs[(size_t)r * W + pc] = z[r * kLDC + lc];
+    Zs[zs_row(r) + pc] = z[r * kLDC + lc];
   }
   cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
   for (int k = 0; k < NBc; ++k) {
     const int lr = k * RBc + br;
-    z[lr * kLDR + c] = Zs[(size_t)(r0 + lr) * W + c];
+    z[lr * kLDR + c] = Zs[zs_row(r0 + lr) + c];
   }
   __syncthreads();
   fft_lines<256, kSR, +1, kCNT, 1, kLDR>(z, tw, tid);
@@ -123,8 +134,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
 
   for (int64_t p = blockIdx.x / kCL; p < prm.P; p += ncl) {
     float* base = prm.scratch + (size_t)(blockIdx.x / kCL) * prm.cluster_stride;
-    float2* Zs = reinterpret_cast<float2*>(base);
-    float* ubuf0 = base + 2 * (size_t)N;
+    float* ubuf0 = base;
     float* ubuf1 = ubuf0 + 2 * (size_t)N;
     float* m0s = ubuf1 + 2 * (size_t)N;
     unsigned long long* bins = reinterpret_cast<unsigned long long*>(m0s + 2 * (size_t)N);   // sums[n], then counts
@@ -144,7 +154,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
     }
     __syncthreads();
     if (!a.v0_is_momentum) {
-      cluster_fluid<false>(cluster, z, tw, cs, Zs, fp, tid, rk, r0, c, br, lc, q, pc);
+      cluster_fluid<false>(cluster, z, tw, cs, reinterpret_cast<float2*>(ubuf0), fp, tid, rk, r0, c, br, lc, q, pc);
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, i = (r0 + lr) * W + c;
         const float2 v = z[lr * kLDR + c];
@@ -174,9 +184,10 @@ shoot_cluster_kernel(const ClusterParams prm) {
         }
         __syncthreads();
       }
-      cluster_fluid<true>(cluster, z, tw, cs, Zs, fp, tid, rk, r0, c, br, lc, q, pc);                                     // v = sharp(m), slab in z
       float* unext = (((S - (s + 1)) & 1) == 0) ? uout : ((s & 1) ? ubuf1 : ubuf0);
       if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * prm.P + p) * 2 * N : uout;
+      // v = sharp(m), slab in z; the spectrum is exchanged through the memory of u_{s+1} (see zs_row)
+      cluster_fluid<true>(cluster, z, tw, cs, reinterpret_cast<float2*>(unext), fp, tid, rk, r0, c, br, lc, q, pc);
       float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * prm.P + p) * 2 * N : nullptr;
       float* utraj0 = (a.traj && s == 0) ? a.traj + (size_t)p * 2 * N : nullptr;
       float* velout = (s == 0 && a.vel) ? a.vel + (size_t)p * 2 * N : nullptr;
@@ -294,7 +305,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
 
 constexpr size_t kClusterSmem = sizeof(float2) * ((size_t)kCH * kLDC + 512 + 32);   // z + twiddles + symbol LUT + reduction scratch
 
-static size_t cluster_scratch_floats() { return (size_t)8 * kCN + 4 * kMaxSectors; }   // Zs(2) + u(2x2) + m0(2) fields + bins
+static size_t cluster_scratch_floats() { return (size_t)6 * kCN + 4 * kMaxSectors; }   // u(2x2) + m0(2) fields + bins
 
 template <int BG>
 static int cluster_max_active(int* out) {
