@@ -141,8 +141,10 @@ shoot_cluster_kernel(const ClusterParams prm) {
     const int64_t b = p / a.T1;
     const int t = (int)(p % a.T1);
     const float* v0p = a.v0 + (size_t)p * 2 * N;
-    float* m0g = (a.m0 && !a.v0_is_momentum) ? a.m0 + (size_t)p * 2 * N : m0s;
-    const float* m0r = a.v0_is_momentum ? v0p : m0g;
+    // The fields the gathers re-read every step (m0, u_s) stay in the per-cluster scratch (fixed addresses, L2-resident);
+    // the caller's output tensors are write-only streams.
+    float* m0out = (a.m0 && !a.v0_is_momentum) ? a.m0 + (size_t)p * 2 * N : nullptr;
+    const float* m0r = m0s;
     float* uout = a.u + (size_t)p * 2 * N;
     float* lpart = reinterpret_cast<float*>(bins) + 3 * kMaxSectors;   // 4 x {sq, vm} partials of the loss epilogue
 
@@ -150,7 +152,9 @@ shoot_cluster_kernel(const ClusterParams prm) {
     // ---- load v0 (or m0) slab, m0 = flat(v0)
     for (int k = 0; k < NBc; ++k) {
       const int lr = k * RBc + br, i = (r0 + lr) * W + c;
-      z[lr * kLDR + c] = make_float2(__ldg(v0p + i), __ldg(v0p + N + i));
+      const float2 v = make_float2(__ldg(v0p + i), __ldg(v0p + N + i));
+      z[lr * kLDR + c] = v;
+      if (a.v0_is_momentum) { m0s[i] = v.x; m0s[N + i] = v.y; }
     }
     __syncthreads();
     if (!a.v0_is_momentum) {
@@ -158,8 +162,9 @@ shoot_cluster_kernel(const ClusterParams prm) {
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, i = (r0 + lr) * W + c;
         const float2 v = z[lr * kLDR + c];
-        m0g[i] = v.x;
-        m0g[N + i] = v.y;
+        m0s[i] = v.x;
+        m0s[N + i] = v.y;
+        if (m0out) { m0out[i] = v.x; m0out[N + i] = v.y; }
       }
       __syncthreads();
     }
@@ -184,8 +189,8 @@ shoot_cluster_kernel(const ClusterParams prm) {
         }
         __syncthreads();
       }
-      float* unext = (((S - (s + 1)) & 1) == 0) ? uout : ((s & 1) ? ubuf1 : ubuf0);
-      if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * prm.P + p) * 2 * N : uout;
+      float* unext = (s + 1 == S) ? uout : ((s & 1) ? ubuf1 : ubuf0);
+      if (a.traj && s + 1 < S) unext = a.traj + ((size_t)((s + 1) * 2 + 0) * prm.P + p) * 2 * N;
       // v = sharp(m), slab in z; the spectrum is exchanged through the memory of u_{s+1} (see zs_row)
       cluster_fluid<true>(cluster, z, tw, cs, reinterpret_cast<float2*>(unext), fp, tid, rk, r0, c, br, lc, q, pc);
       float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * prm.P + p) * 2 * N : nullptr;
