@@ -338,9 +338,9 @@ class HostPipeline:
         self.chunk = max(1, min(int(chunk_slices), B))
         self.copy_stream = torch.cuda.Stream(self.dev)
         dev, T1, cs = self.dev, self.T1, self.chunk
-        self.pack_masks = bool(pack_masks) and (T * H * W) % 4 == 0
+        import os
+        self.pack_masks = bool(pack_masks) and (T * H * W) % 4 == 0 and os.environ.get("B2_PACK_MASKS") != "0"
         if int(pack_threads) <= 0:    # CPUs this process may use, shared with the other ranks of the node
-            import os
             try:
                 ncpu = len(os.sched_getaffinity(0))
             except (AttributeError, OSError):
@@ -352,7 +352,7 @@ class HostPipeline:
             # ranks for cores.  Measured on the 8-GPU box (32 host CPUs): 1 or 2 ranks (>= 12 threads each) gain 25 %
             # (5.6 -> 4.25-4.4 ms per step); 4 ranks with 8 threads each lose (6.9 vs 5.9-6.4 ms) and 8 ranks with 4
             # threads lose (15.3 vs 13.3 ms), so ranks with fewer than 12 host threads copy fp32.
-            if share < 12:
+            if share < 12 and os.environ.get("B2_PACK_MASKS") != "1":      # B2_PACK_MASKS=1 forces the narrowing
                 self.pack_masks = False
         self.pack_threads = int(pack_threads)
         self.h2d_bytes = 0
