@@ -348,7 +348,7 @@ static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
 #define B2_BWD_U1 4
 #endif
 #ifndef B2_BWD_U3A
-#define B2_BWD_U3A 4
+#define B2_BWD_U3A 8
 #endif
 #ifndef B2_BWD_U3B
 #define B2_BWD_U3B 2
