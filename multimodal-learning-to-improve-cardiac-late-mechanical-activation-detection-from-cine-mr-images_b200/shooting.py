@@ -10,6 +10,7 @@ trajectory (``b2_shoot_bwd``).
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import torch
 from torch.autograd.function import once_differentiable
@@ -355,6 +356,9 @@ class HostPipeline:
             if share < 12 and os.environ.get("B2_PACK_MASKS") != "1":      # B2_PACK_MASKS=1 forces the narrowing
                 self.pack_masks = False
         self.pack_threads = int(pack_threads)
+        self._pack_s = self._pack_budget_s = 0.0
+        self._pack_chunks = 0
+        self._pack_forced = os.environ.get("B2_PACK_MASKS") == "1"
         self.h2d_bytes = 0
         # Three staging buffers: with two, the copy of chunk i+1 has to wait for the kernel of chunk i-1, which ends
         # just about when the copy of chunk i does (kernel and copy times per chunk are nearly equal) - any jitter
@@ -404,11 +408,19 @@ class HostPipeline:
                         if st["used"]:
                             st["ready"].synchronize()        # the copy out of this pinned pack buffer has finished
                         # CPU pass (GIL released inside the call) while the v0 copy above occupies the bus
+                        t_pack = time.perf_counter()
                         rc = lib().b2_pack_binary_u8_host(C.c_void_p(vol_host[b0:b1].data_ptr()),
                                                           C.c_void_p(st["pack_host"].data_ptr()), n, self.pack_threads)
                         if rc < 0:
                             check(rc, "b2_pack_binary_u8_host")
                         packed = rc == 1
+                        # safety net: the pass only pays while it hides behind the v0 copy of the same chunk
+                        # (~50 GB/s over PCIe); a starved host (few or busy cores) switches it off for later calls
+                        self._pack_s += time.perf_counter() - t_pack
+                        self._pack_budget_s += 0.8 * (nb * T1 * 2 * H * W * 4) / 50e9
+                        self._pack_chunks += 1
+                        if self._pack_chunks >= 16 and self._pack_s > self._pack_budget_s and not self._pack_forced:
+                            self.pack_masks = False
                     if packed:
                         st["vol_u8"][:n].copy_(st["pack_host"][:n], non_blocking=True)
                         check(lib().b2_unpack_u8(ptr(st["vol_u8"]), ptr(st["vol"]), n,
