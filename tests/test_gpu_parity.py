@@ -111,18 +111,28 @@ def test_shoot_step_parity(pkg, oracle, dev, S):
     assert relerr(vz.grad, vc.grad) < 5e-5
 
 
-def test_zero_background_shooting(pkg, oracle, dev):
-    """D1-alt (zero background) through the fused kernel."""
-    H = W = 32
-    S = 3
+@pytest.mark.parametrize("hw,S", [((32, 32), 3), ((128, 128), 4), ((256, 256), 2), ((64, 128), 3)])
+def test_zero_background_shooting(pkg, oracle, dev, hw, S):
+    """D1-alt (zero background) through the single-CTA kernel, the 4-CTA cluster kernel and the op-level path;
+    a large velocity so that the geodesic really samples outside the grid."""
+    H, W = hw
     src_vol, tar_vol = _masks(pkg, 2, 3, H, W)
-    v0 = _smooth_v0(pkg, 4, H, W, 34, 3.0)
+    v0 = _smooth_v0(pkg, 4, H, W, 34, 6.0)
     conv = oracle.Conventions(background="zero")
     ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, conv=conv)
     out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S,
                                 background="zero")
-    for k in ("momentum", "velocity", "displacement", "deformed_source"):
-        assert relerr(out[k], ref[k]) < TOL, f"{k}: {relerr(out[k], ref[k]):.2e}"
+    ref64 = oracle.forward_volume(v0.double(), src_vol.double(), tar_vol.double(), oracle.FluidMetric(PARAMS), S, conv=conv)
+    # Fields that leave the grid under the zero rule are discontinuous at the border, so at this amplitude the fp32
+    # oracle itself is 0.5-1.5e-5 away from its float64 run: the CUDA path is held to the float64 truth within twice
+    # that, and to the fp32 oracle within three times that.
+    for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
+        own = relerr(ref[k], ref64[k])
+        assert relerr(out[k], ref64[k]) < max(TOL, 2.0 * own), f"{k} vs f64: {relerr(out[k], ref64[k]):.2e} (oracle32: {own:.2e})"
+        assert relerr(out[k], ref[k]) < max(TOL, 3.0 * own), f"{k}: {relerr(out[k], ref[k]):.2e} (oracle32 vs 64: {own:.2e})"
+    # the zero rule really differs from the clamp rule on this input
+    clamp = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S)
+    assert relerr(clamp["displacement"], out["displacement"]) > 1e-4
 
 
 def test_errors_on_gpu(pkg, dev):
