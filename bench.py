@@ -14,9 +14,13 @@ data-path collective).  A "step" is one pass of the hot path over that batch.
              D2H of the strain matrices inside the timed region
 * roofline : algorithmic bytes (700*N per pair) / duration of the fused
              shooting kernel, against MEASURED_PEAKS.json hbm_gbs
-* cpu_baseline : the torch-CPU oracle (a port: the reference's own lagomorph path is not runnable)
+* cpu_baseline : the plain-C OpenMP oracle (a port: the reference's own lagomorph path is not runnable)
              on a bounded sample, rank 0, N=1 only
-`--impl reference` times that same CPU oracle with all host threads (the reference's CPU path).
+* extra    : the other BASELINE.json configs measured in the same run on the same ranks (short step counts):
+             c3_train (configs[2]), c4_sharded (configs[3], strong-sharded over the N ranks), c5_step (configs[4],
+             full training step with the NCCL gradient all-reduce)
+`--impl reference` times that same CPU oracle with all host threads (the reference's CPU path); the thread count
+is passed explicitly, so torchrun's OMP_NUM_THREADS=1 does not shrink it.
 """
 from __future__ import annotations
 
@@ -50,6 +54,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-slices", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2]/[3]/[4] measurements")
     return ap.parse_args()
 
 
@@ -62,11 +67,25 @@ def workload_config(n_gpus):
             "l2_policy": "inputs larger than L2 (v0 201 MB + masks 105 MB per step vs 126 MB L2)"}
 
 
+def kernel_source_digest():
+    """sha256 over the sources the dominant kernel is compiled from: stamps profiles/traffic.json."""
+    import hashlib
+    csrc = next(ROOT.glob("*_b200")) / "csrc"
+    h = hashlib.sha256()
+    for name in ("shoot.cu", "fft.cuh", "common.cuh", "strain.cuh"):
+        h.update((csrc / name).read_bytes())
+    return h.hexdigest()
+
+
 def measured_traffic():
-    """dram__bytes_read+write per launch of the fused kernel from the committed ncu capture (profiles/)."""
+    """dram__bytes_read+write per launch of the fused kernel from the committed ncu capture (profiles/).  The capture
+    is stamped with the digest of the kernel's sources: when they have changed since, the number is stale -> None."""
     p = ROOT / "profiles" / "traffic.json"
     try:
-        return int(json.loads(p.read_text())["traffic_bytes_per_launch"])
+        rec = json.loads(p.read_text())
+        if rec.get("kernel_source_sha256") != kernel_source_digest():
+            return None
+        return int(rec["traffic_bytes_per_launch"])
     except Exception:
         return None
 
@@ -158,12 +177,14 @@ def cpu_forward(pkg, n_slices):
     Preferred: the plain-C OpenMP oracle (oracle/lddmm_c.c) on all host threads; fallback: the torch-CPU oracle.
     Both are ports: the reference's own lagomorph CPU path is not runnable."""
     import oracle
-    threads = os.cpu_count() or 1
+    try:                      # the host threads this process may run on; NOT OMP_NUM_THREADS (torchrun sets it to 1)
+        threads = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        threads = os.cpu_count() or 1
     vol, v0 = make_inputs(pkg, n_slices, seed=2434)
     try:
         from oracle import c_oracle
         c_oracle.lib()
-        threads = min(threads, c_oracle.max_threads()) if c_oracle.max_threads() > 0 else threads
 
         def run():
             return c_oracle.forward_volume(v0, vol, PARAMS, S_STEPS, N_SECTORS, N_FRAMES, nthreads=threads)
@@ -263,26 +284,40 @@ def main():
             return pkg.shoot_warp_strain(v0_d, src_vol, tar_vol, metric, num_steps=S_STEPS,
                                          n_sectors=N_SECTORS, n_frames=N_FRAMES)
 
-    h2d = vol_h.numel() * 4 + v0_h.numel() * 4          # replaced below by what the pipeline really copies
     d2h = B * N_SECTORS * N_FRAMES * 4
 
     # public host-buffer API: pinned host inputs -> strain matrices on the host; H2D of slice chunks on a
-    # copy stream overlaps the fused kernel of the previous chunk
+    # copy stream overlaps the fused kernel of the previous chunk.  The cine masks are binary (README.md:21) and are
+    # handed over as uint8 (one byte per pixel over PCIe, widened on the device; no host pass), v0 as fp32.
+    vol_u8_h = vol_h.to(torch.uint8).pin_memory()
     pipe = pkg.HostPipeline(B, T_FRAMES, H, W, metric, num_steps=S_STEPS, n_sectors=N_SECTORS, n_frames=N_FRAMES,
                             device=dev)          # default chunking: four equal chunks of 16 slices
+    pending = []
 
     def step_e2e():
-        return pipe(v0_h, vol_h)
+        # streaming use of the public API: submit step i, then wait for step i-1's strain matrices on the host
+        # (every step's result is host-visible inside the timed region; uploads of step i overlap kernels of i-1)
+        pending.append(pipe.submit(v0_h, vol_u8_h))
+        if len(pending) > 1:
+            pending.pop(0).get()
 
-    def timed(fn, steps, warmup):
+    def drain_e2e():
+        while pending:
+            pending.pop(0).get()
+
+    def timed(fn, steps, warmup, after=None):
         for _ in range(warmup):
             fn()
+        if after:
+            after()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = pkg._lib.launches()
         e0.record()
         for _ in range(steps):
             fn()
+        if after:
+            after()                                     # host sync on the last result, then the closing event
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -305,18 +340,31 @@ def main():
     sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3), after=drain_e2e)
     h2d = int(pipe.h2d_bytes)                            # v0 as fp32 + binary masks as one byte per pixel
+
+    # ---- H2D ceiling of this box at N ranks: the same byte count per rank as ONE plain pinned cudaMemcpyAsync per
+    # step, all ranks copying at once (nothing else running) - what the host -> device leg alone allows
+    ceil_h = torch.empty(h2d, dtype=torch.uint8).pin_memory()
+    ceil_d = torch.empty(h2d, dtype=torch.uint8, device=dev)
+
+    def step_copy():
+        ceil_d.copy_(ceil_h, non_blocking=True)
+
+    ms_copy, _ = timed(step_copy, args.steps, 3)
+    del ceil_h, ceil_d
 
     # ---- roofline of the dominant kernel: direct C-ABI launches of the fused shooting kernel
     out = step_resident()
     mom = pkg.strain.mask_moments(src_vol[:, 0, 0].contiguous())
-    tab = pkg.strain.sector_table(N_SECTORS, dev)
+    frame = pkg.strain.Frame(N_SECTORS, B, dev)
+    fs = frame.c_struct()
     a = pkg._lib.ShootArgs()
     tar_flat = tar_vol.reshape(P, 1, H, W).contiguous()
     src0 = src_vol[:, :, 0].contiguous()
     counts = torch.empty((B, N_SECTORS, T1), dtype=torch.int32, device=dev)
-    a.v0, a.src, a.tar, a.moments, a.table = v0_d.data_ptr(), src0.data_ptr(), tar_flat.data_ptr(), mom.data_ptr(), tab.data_ptr()
+    a.v0, a.src, a.tar, a.moments, a.table = v0_d.data_ptr(), src0.data_ptr(), tar_flat.data_ptr(), mom.data_ptr(), fs.table
+    a.table_slice_stride, a.theta0, a.clockwise, a.flags = fs.table_slice_stride, fs.theta0, fs.clockwise, 0
     a.m0, a.vel, a.u = out["momentum"].data_ptr(), out["velocity"].data_ptr(), out["displacement"].data_ptr()
     a.sdef, a.S, a.counts, a.traj = out["deformed_source"].data_ptr(), out["strain_matrix"].data_ptr(), counts.data_ptr(), None
     a.B, a.T1, a.H, a.W = B, T1, H, W
@@ -334,11 +382,31 @@ def main():
     peak, peak_src = peaks()
     k_ms = ms_kernel / args.steps
     achieved = P * BYTES_PER_PAIR / (k_ms * 1e-3) / 1e9
+    del out, ws, tar_flat, counts, pipe
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, same run, same ranks (short step counts)
+    extra = None
+    if not args.no_extras:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_configs as bc
+        extra = {}
+        for name, fn in (("c3_train", lambda: bc.c3_train(pkg, dev, fused=True, dist=dist)),
+                         ("c4_sharded", lambda: bc.c4_sharded(pkg, dev, dist=dist)),
+                         ("c5_step", lambda: bc.c5_step(pkg, dev, dist=dist))):
+            try:
+                extra[name] = fn()
+            except Exception as e:                      # an extra must never take the headline line down
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         n = world
         value = n * P * args.steps / (ms_total * 1e-3)
         e2e_value = n * P * args.steps / (ms_e2e * 1e-3)
+        copy_ms = ms_copy / args.steps
+        ceil_gbs = n * h2d / (copy_ms * 1e-3) / 1e9
+        e2e_gbs = n * h2d / (ms_e2e / args.steps * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -346,15 +414,22 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps,
-                        "host_inputs": "pinned fp32 v0 + fp32 cine masks; the masks are verified binary by a host "
-                                       "pass and cross PCIe as one byte per pixel (lossless), v0 as fp32"},
+                        "h2d_ceiling_gbs": ceil_gbs, "h2d_achieved_gbs": e2e_gbs, "frac_of_h2d_ceiling": e2e_gbs / ceil_gbs,
+                        "h2d_ceiling_note": f"aggregate over {n} rank(s): {h2d} B per rank per step as one plain pinned "
+                                            "cudaMemcpyAsync, all ranks at once, measured in this run",
+                        "host_inputs": "pinned host tensors: fp32 v0 + uint8 binary cine masks (1 B per pixel, widened on "
+                                       "the device); strain matrices back on the host, every step's result waited for "
+                                       "inside the timed region (HostPipeline.submit / PipelineResult.get)"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "shoot_fwd_kernel<128,128,1024,clamp> (fused flat + 10 EPDiff steps + warp + strain)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": measured_traffic(), "peak_source": peak_src, "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": P * BYTES_PER_PAIR,
                              "note": "op-level algorithmic bytes (700*N per pair); the fused kernel keeps m/v on chip, "
-                                     "so real DRAM traffic is far lower (see profiles/)"}}
+                                     "so real DRAM traffic is far lower (see profiles/); traffic is null when the kernel "
+                                     "sources changed since the ncu capture in profiles/traffic.json"}}
+        if extra is not None:
+            line["extra"] = extra
         if n == 1 and not args.no_cpu_baseline:
             cpu_v, what, threads = cpu_pairs_per_s(pkg, args.cpu_sample_slices, 3)
             line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -43,6 +43,26 @@ extern "C" {
 #define B2_BG_CLAMP 0
 #define B2_BG_ZERO 1
 
+/* Path selection is explicit (no environment variables are read anywhere in the library): `flags` of
+ * b2_shoot_args / b2_shoot_bwd_args and of the *_flags workspace queries. */
+#define B2_FLAG_OPLEVEL 1    /* run the op-level kernel sequence (path B) even where a fused kernel exists */
+
+/* ---- sector frame of a slice (DENSE_utils.py:196-204 of the reference: spl2patchSA) ----
+ * The reference's 126-sector mesh starts at theta0 = arctan2(PositionB - PositionA) and runs clockwise or
+ * counter-clockwise per subject.  With theta = atan2(d_row, d_col) about the frame-0 mask centroid:
+ *   clockwise != 0 (default):  sector = floor(((theta - theta0) mod 2 pi) / (2 pi / n))
+ *   clockwise == 0          :  sector = n - 1 - (that index)
+ * Integer-exact: `table` holds the Q20 boundary directions ALREADY ROTATED by theta0 on the host
+ * (b2_sector_table_rotated_host), one (n_sectors,2) table per slice `table_slice_stride` int32 apart
+ * (0 = one table shared by all slices); `theta0` (B floats, device) only seeds the search and may be NULL
+ * when every table is unrotated; `clockwise` (B int32, device) NULL = all clockwise. */
+typedef struct b2_sector_frame {
+  const int32_t* table;
+  int64_t table_slice_stride;
+  const float* theta0;
+  const int32_t* clockwise;
+} b2_sector_frame;
+
 int b2_version(void);
 const char* b2_error_string(int code);
 
@@ -107,11 +127,16 @@ int b2_fluid_apply(const float* f, float* out, int64_t P, int64_t H, int64_t W,
 /* ---- sectors ([SPEC]; count/order pinned by DENSE_utils.py:177-295, affine.py:52-87) ----
  * Host helper: Q20 boundary directions (row, col) for n_sectors wedges. */
 int b2_sector_table_host(int n_sectors, int32_t* table_host /* 2*n_sectors */);
+/* Same with every boundary rotated by theta0 (radians): b_k = round(2^20 (sin, cos)(theta0 + 2 pi k / n)). */
+int b2_sector_table_rotated_host(int n_sectors, double theta0, int32_t* table_host /* 2*n_sectors */);
 /* moments (B,3) int64 = {count, sum(row), sum(col)} of mask0 > 0.5; zero-filled by the call. */
 int b2_mask_moments(const float* mask0, int64_t* moments, int64_t B, int64_t H, int64_t W,
                     void* stream);
 int b2_sector_map_i32(const int64_t* moments, const int32_t* table, int32_t* sector,
                       int64_t B, int64_t H, int64_t W, int n_sectors, void* stream);
+/* per-slice sector frame (theta0 / direction); frame->table must not be NULL */
+int b2_sector_map_i32_ex(const int64_t* moments, const b2_sector_frame* frame, int32_t* sector,
+                         int64_t B, int64_t H, int64_t W, int n_sectors, void* stream);
 
 /* ---- strain matrix ([SPEC] SURVEY.md A.7/A.8) ----
  * u (B,T1,2,H,W), tar (B,T1,H,W) masks, moments (B,3).  S (B,1,n_sectors,n_frames):
@@ -126,6 +151,15 @@ int b2_strain_sector_bwd(const float* gS, const float* u, const float* tar,
                          const int64_t* moments, const int32_t* table, const int32_t* counts,
                          float* du, int64_t B, int64_t T1, int64_t H, int64_t W,
                          int n_sectors, int n_frames, void* stream);
+/* same two with a per-slice sector frame */
+int b2_strain_sector_fwd_ex(const float* u, const float* tar, const int64_t* moments,
+                            const b2_sector_frame* frame, float* S, int32_t* counts,
+                            int64_t B, int64_t T1, int64_t H, int64_t W,
+                            int n_sectors, int n_frames, void* stream);
+int b2_strain_sector_bwd_ex(const float* gS, const float* u, const float* tar,
+                            const int64_t* moments, const b2_sector_frame* frame, const int32_t* counts,
+                            float* du, int64_t B, int64_t T1, int64_t H, int64_t W,
+                            int n_sectors, int n_frames, void* stream);
 
 /* ---- fused geodesic shooting: flat + S x EPDiff_step (+ warp + strain) ----
  * Replaces m0 = metric.flat(v0); u = lagomorph.expmap(metric, m0, T, num_steps);
@@ -168,10 +202,17 @@ typedef struct b2_shoot_args {
                               reductions of RegistrationReconstructionLoss (registration_losses.py:25-26) taken
                               inside the shooting kernel (fixed summation order: bitwise reproducible).  Needs
                               src and tar; on the op-level path (rectangular grids) also the sdef and vel outputs. */
+  /* sector frame of every slice (see b2_sector_frame): `table` above is read with this stride; all optional */
+  int64_t table_slice_stride;
+  const float* theta0;
+  const int32_t* clockwise;
+  int32_t flags;           /* B2_FLAG_* */
+  int32_t reserved_;
 } b2_shoot_args;
 int64_t b2_sizeof_shoot_args(void);   /* ABI check for bindings that mirror the struct */
 
-int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps);
+int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps);   /* flags = 0 */
+int64_t b2_shoot_workspace_bytes_flags(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps, int flags);
 int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Adjoint of b2_shoot_fwd through expmap and flat: given gu = dL/du^S (NULL = 0),
@@ -190,6 +231,26 @@ int b2_shoot_bwd_loss(const float* gu, const float* gvel, const float* gm0, cons
                       const float* m0, const float* traj, float* gv0, int64_t P, int64_t H, int64_t W,
                       int num_steps, float alpha, float beta, float gamma, float T, int background,
                       int v0_is_momentum, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Struct form of the same call with explicit path flags.  Fused adjoint kernels exist for square grids of
+ * 16..128 (one CTA per frame-pair) and 256x256 (one 4-CTA cluster per frame-pair); other sizes, B2_FLAG_OPLEVEL,
+ * or a device that cannot co-schedule the cluster run the op-level sweep.  The workspace is sized per path:
+ * resident CTAs x 3 fields (fused), 5 P fields + FFT scratch (op-level). */
+typedef struct b2_shoot_bwd_args {
+  const float* gu;      /* dL/du^S (P,2,H,W) or NULL */
+  const float* gvel;    /* dL/dvel or NULL */
+  const float* gm0;     /* explicit dL/dm0 or NULL */
+  const float* g_reg;   /* (P) dL/d(sum vel . m0) or NULL */
+  const float* m0;
+  const float* traj;
+  float* gv0;
+  int64_t P, H, W;
+  int32_t num_steps, background, v0_is_momentum, flags;
+  float alpha, beta, gamma, T;
+} b2_shoot_bwd_args;
+int64_t b2_sizeof_shoot_bwd_args(void);
+int64_t b2_shoot_bwd_workspace_bytes_flags(int64_t P, int64_t H, int64_t W, int flags);
+int b2_shoot_bwd_ex(const b2_shoot_bwd_args* args, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- loss epilogue of the path (RegistrationReconstructionLoss, registration_losses.py:22-28) ----
  * Op-level form of b2_shoot_args.loss_terms: terms (P,2) = {sum_x (tar - sdef)^2, sum_x vel . m0} per pair from
@@ -222,6 +283,11 @@ int b2_roll_rows(const float* S, float* out, const int32_t* n, int64_t B, int64_
  * zero-fills out first). */
 int b2_regroup_pairs(const float* u, const int32_t* pair_slot, float* out, int64_t P, int64_t n_slices,
                      int64_t F, int64_t C, int64_t H, int64_t W, void* stream);
+/* Adjoint (the reference builds this tensor with differentiable stack / permute / pad and backpropagates the LMA
+ * loss through it, joint_registration_regression_trainer.py:290-320): gu[p] = gout[pair_slot[p]], zero for a
+ * dropped pair. */
+int b2_regroup_pairs_bwd(const float* gout, const int32_t* pair_slot, float* gu, int64_t P, int64_t n_slices,
+                         int64_t F, int64_t C, int64_t H, int64_t W, void* stream);
 
 /* ---- binary masks over PCIe as one byte per pixel (host-buffer entry point) ----
  * The reference's cine inputs are fp32 volumes holding exactly 0 or 1 (README.md:21, joint_dataset.py:61-89).

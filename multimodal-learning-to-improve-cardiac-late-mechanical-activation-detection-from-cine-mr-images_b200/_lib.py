@@ -35,7 +35,29 @@ class ShootArgs(C.Structure):
         ("n_sectors", C.c_int32), ("n_frames", C.c_int32), ("background", C.c_int32),
         ("alpha", C.c_float), ("beta", C.c_float), ("gamma", C.c_float), ("T", C.c_float),
         ("loss_terms", C.c_void_p),
+        ("table_slice_stride", C.c_int64), ("theta0", C.c_void_p), ("clockwise", C.c_void_p),
+        ("flags", C.c_int32), ("reserved_", C.c_int32),
     ]
+
+
+class SectorFrame(C.Structure):
+    """Mirror of ``b2_sector_frame``: per-slice rotated boundary tables + search seed + direction."""
+    _fields_ = [("table", C.c_void_p), ("table_slice_stride", C.c_int64), ("theta0", C.c_void_p),
+                ("clockwise", C.c_void_p)]
+
+
+class ShootBwdArgs(C.Structure):
+    """Mirror of ``b2_shoot_bwd_args``."""
+    _fields_ = [
+        ("gu", C.c_void_p), ("gvel", C.c_void_p), ("gm0", C.c_void_p), ("g_reg", C.c_void_p),
+        ("m0", C.c_void_p), ("traj", C.c_void_p), ("gv0", C.c_void_p),
+        ("P", C.c_int64), ("H", C.c_int64), ("W", C.c_int64),
+        ("num_steps", C.c_int32), ("background", C.c_int32), ("v0_is_momentum", C.c_int32), ("flags", C.c_int32),
+        ("alpha", C.c_float), ("beta", C.c_float), ("gamma", C.c_float), ("T", C.c_float),
+    ]
+
+
+FLAG_OPLEVEL = 1      # B2_FLAG_OPLEVEL
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
@@ -56,6 +78,16 @@ SIGNATURES = {
     "b2_fluid_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "b2_fluid_apply": (c_int, [c_f, c_f, c_i64, c_i64, c_i64, c_float, c_float, c_float, c_int, c_f, c_i64, c_f]),
     "b2_sector_table_host": (c_int, [c_int, C.POINTER(C.c_int32)]),
+    "b2_sector_table_rotated_host": (c_int, [c_int, C.c_double, C.POINTER(C.c_int32)]),
+    "b2_sector_map_i32_ex": (c_int, [c_f, C.POINTER(SectorFrame), c_f, c_i64, c_i64, c_i64, c_int, c_f]),
+    "b2_strain_sector_fwd_ex": (c_int, [c_f, c_f, c_f, C.POINTER(SectorFrame), c_f, c_f, c_i64, c_i64, c_i64, c_i64,
+                                        c_int, c_int, c_f]),
+    "b2_strain_sector_bwd_ex": (c_int, [c_f, c_f, c_f, c_f, C.POINTER(SectorFrame), c_f, c_f, c_i64, c_i64, c_i64,
+                                        c_i64, c_int, c_int, c_f]),
+    "b2_shoot_workspace_bytes_flags": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_int, c_int]),
+    "b2_shoot_bwd_workspace_bytes_flags": (c_i64, [c_i64, c_i64, c_i64, c_int]),
+    "b2_shoot_bwd_ex": (c_int, [C.POINTER(ShootBwdArgs), c_f, c_i64, c_f]),
+    "b2_sizeof_shoot_bwd_args": (c_i64, []),
     "b2_mask_moments": (c_int, [c_f, c_f, c_i64, c_i64, c_i64, c_f]),
     "b2_sector_map_i32": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_int, c_f]),
     "b2_strain_sector_fwd": (c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_f]),
@@ -74,6 +106,7 @@ SIGNATURES = {
     "b2_augment_volume": (c_int, [c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f]),
     "b2_roll_rows": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_f]),
     "b2_regroup_pairs": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f]),
+    "b2_regroup_pairs_bwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f]),
     "b2_pack_binary_u8_host": (c_int, [c_f, c_f, c_i64, c_int]),
     "b2_unpack_u8": (c_int, [c_f, c_f, c_i64, c_f]),
     "b2_device_sm_count": (c_int, [c_int]),
@@ -97,9 +130,11 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.b2_sizeof_shoot_args() != C.sizeof(ShootArgs):
-            raise RuntimeError(f"{_LIB_PATH}: b2_shoot_args is {L.b2_sizeof_shoot_args()} bytes in the library, "
-                               f"{C.sizeof(ShootArgs)} in the binding - rebuild with `python __graft_entry__.py`")
+        for what, have, want in (("b2_shoot_args", L.b2_sizeof_shoot_args(), C.sizeof(ShootArgs)),
+                                 ("b2_shoot_bwd_args", L.b2_sizeof_shoot_bwd_args(), C.sizeof(ShootBwdArgs))):
+            if have != want:
+                raise RuntimeError(f"{_LIB_PATH}: {what} is {have} bytes in the library, {want} in the binding - "
+                                   "rebuild with `python __graft_entry__.py`")
         _lib = L
     return _lib
 
@@ -118,12 +153,47 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """The caller's current stream ON ``device`` (default: the current device) as a ``cudaStream_t``."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def device_guard(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current, so that ``stream()`` and every
+    launch inside target the tensors' device even when another device is current (multi-GPU processes)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+    return wrapped
+
+
+class on_device:
+    """``with on_device(t_or_dev):`` makes the tensors' device current for the launches inside, so a call on
+    cuda:1 tensors while cuda:0 is current launches on cuda:1's context and ITS current stream."""
+
+    def __init__(self, dev):
+        if isinstance(dev, torch.Tensor):
+            dev = dev.device
+        self._g = torch.cuda.device(dev)
+
+    def __enter__(self):
+        self._g.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self._g.__exit__(*exc)
 
 
 def require_cuda(*tensors, dtype=torch.float32):  # noqa: C901
-    """All tensors must be contiguous CUDA tensors of one device (no CPU fallback)."""
+    """All tensors must be contiguous CUDA tensors of one device (no CPU fallback).  Returns that device."""
     dev = None
     for t in tensors:
         if t is None:

@@ -121,6 +121,56 @@ __device__ __forceinline__ void tap_grad(const Taps& t, float v00, float v10, fl
   g1 = (1.f - t.a) * (v01 - v00) + t.a * (v11 - v10);
 }
 
+// ---------------------------------------------------------------------------
+// Pre-aggregated two-plane splat (adjoint of the bilinear gather) for threads that walk CONSECUTIVE rows of
+// one column with the lanes of a warp along consecutive columns.  For smooth displacements the 2x2 footprints
+// of neighbouring pixels overlap: the right column of lane L is the left column of lane L+1, and the bottom row
+// of pixel (r, c) is the top row of pixel (r+1, c).  The right-column contributions are handed to lane L+1 by
+// warp shuffle and the bottom-row contributions are carried in registers to the thread's next row, so a pixel
+// issues ~1 RED per plane instead of 4 (index compares decide: any mismatch - floor crossing, image edge, warp
+// edge - falls back to direct atomics, so the sum is always complete).  All 32 lanes must call converged.
+// ---------------------------------------------------------------------------
+struct SplatCarry {
+  int idx;       // flat target index of the carried bottom-left contribution, -1 = empty
+  float a, b;    // plane 0 / plane 1 values
+};
+
+__device__ __forceinline__ void splat_flush(float* __restrict__ G, int plane, SplatCarry& cy) {
+  if (cy.idx >= 0) {
+    atomicAdd(G + cy.idx, cy.a);
+    atomicAdd(G + plane + cy.idx, cy.b);
+  }
+  cy.idx = -1;
+}
+
+template <int BG>
+__device__ __forceinline__ void splat2_agg(float* __restrict__ G, int plane, const Taps& t, float g0, float g1,
+                                           SplatCarry& cy, int lane) {
+  const float oma = 1.f - t.a, omb = 1.f - t.b;
+  float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
+  if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
+  float aT = w00 * g0, bT = w00 * g1;          // (i0, j0)
+  float aB = w10 * g0, bB = w10 * g1;          // (i1, j0)
+  const float aTr = w01 * g0, bTr = w01 * g1;  // (i0, j1)
+  const float aBr = w11 * g0, bBr = w11 * g1;  // (i1, j1)
+  constexpr unsigned full = 0xffffffffu;
+  const int n01 = __shfl_up_sync(full, t.o01, 1), n11 = __shfl_up_sync(full, t.o11, 1);
+  const float naT = __shfl_up_sync(full, aTr, 1), nbT = __shfl_up_sync(full, bTr, 1);
+  const float naB = __shfl_up_sync(full, aBr, 1), nbB = __shfl_up_sync(full, bBr, 1);
+  const bool take = lane > 0 && n01 == t.o00 && n11 == t.o10;     // lane-1's right column is my left column
+  const bool given = (__shfl_down_sync(full, (int)take, 1) != 0) && lane < 31;
+  if (take) { aT += naT; bT += nbT; aB += naB; bB += nbB; }
+  if (!given) {
+    atomicAdd(G + t.o01, aTr); atomicAdd(G + plane + t.o01, bTr);
+    atomicAdd(G + t.o11, aBr); atomicAdd(G + plane + t.o11, bBr);
+  }
+  if (cy.idx == t.o00) { aT += cy.a; bT += cy.b; }
+  else splat_flush(G, plane, cy);
+  atomicAdd(G + t.o00, aT);
+  atomicAdd(G + plane + t.o00, bT);
+  cy.idx = t.o10; cy.a = aB; cy.b = bB;
+}
+
 // Bilinear samples of the two planes f, f+plane at (p0,p1).  Warp-uniform fast path: when every lane's
 // 2x2 footprint lies inside the image, the four taps are base + {0, 1, W, W+1} (immediate offsets from ONE
 // address, no clamps); otherwise the whole warp takes the background-ruled path.  Both paths use the same
@@ -183,12 +233,16 @@ __device__ __forceinline__ float diffT(float qm, float q0, float qp, int k, int 
 
 // ---------------------------------------------------------------------------
 // Sector classification (D7) - integer predicates only.
-// table[2k] = round(2^20 sin(2 pi k/n)), table[2k+1] = round(2^20 cos(2 pi k/n)).
+// table[2k] = round(2^20 sin(theta0 + 2 pi k/n)), table[2k+1] = round(2^20 cos(theta0 + 2 pi k/n)): the boundary
+// directions of the slice's sector frame, rotated on the host (b2_sector_table_rotated_host).  `theta0` only
+// seeds the search (any value gives the same result); `flip` (counter-clockwise numbering of the reference's
+// spl2patchSA mesh, /root/reference/modules/data/utils/DENSE_utils.py:201-204) maps k -> n-1-k.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int classify_sector(long long dr, long long dc, const int32_t* __restrict__ table, int n) {
+__device__ __forceinline__ int classify_sector(long long dr, long long dc, const int32_t* __restrict__ table, int n,
+                                               float theta0 = 0.f, bool flip = false) {
   if (dr == 0 && dc == 0) return -1;
-  float th = atan2f((float)dr, (float)dc);
-  if (th < 0.f) th += 6.283185307179586f;
+  float th = atan2f((float)dr, (float)dc) - theta0;
+  th -= 6.283185307179586f * floorf(th * 0.15915494309189535f);
   int k = (int)floorf(th * ((float)n * 0.15915494309189535f));
   k = min(max(k, 0), n - 1);
   for (int it = 0; it < n; ++it) {
@@ -199,7 +253,22 @@ __device__ __forceinline__ int classify_sector(long long dr, long long dc, const
     else if (hi >= 0) k = k1;
     else break;
   }
-  return k;
+  return flip ? n - 1 - k : k;
+}
+
+// Sector frame of slice b as the kernels use it
+struct SectorFrame {
+  const int32_t* table;   // this slice's (n,2) Q20 boundary table
+  float theta0;
+  bool flip;
+};
+__device__ __forceinline__ SectorFrame sector_frame_of(const int32_t* table, long long table_slice_stride,
+                                                       const float* theta0, const int32_t* clockwise, long long b) {
+  SectorFrame f;
+  f.table = table + (size_t)b * (size_t)table_slice_stride;
+  f.theta0 = theta0 ? theta0[b] : 0.f;
+  f.flip = clockwise ? (clockwise[b] == 0) : false;
+  return f;
 }
 
 // Centroid as float: double division then cast; image centre for an empty mask.

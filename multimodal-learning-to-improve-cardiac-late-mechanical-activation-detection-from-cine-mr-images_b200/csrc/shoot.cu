@@ -20,8 +20,6 @@
 // op-level kernels (HBM-bound per op).
 //
 // Backward: shoot_bwd_kernel (fused EPDiff adjoint, square grids up to 128x128) or the op-level sweep.
-#include <stdlib.h>
-
 #include "fft.cuh"
 #include "strain.cuh"
 
@@ -37,7 +35,16 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
 int cluster_grid_clusters(int64_t P);
 int64_t cluster_workspace_bytes(int64_t P);
 int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t st);
-static bool cluster_size(int64_t H, int64_t W) { return H == 256 && W == 256 && !getenv("B2_NO_CLUSTER"); }
+int64_t cluster_bwd_workspace_bytes(int64_t P);
+struct ShootBwdParams;
+int launch_shoot_cluster_bwd(const ShootBwdParams& prm, int background, cudaStream_t st);
+// 256x256 runs on the cluster kernels unless the caller asks for the op-level path or the device cannot
+// co-schedule a 4-CTA cluster with this much shared memory (then path B serves it)
+static bool cluster_size(int64_t H, int64_t W, int64_t P, int flags) {
+  return H == 256 && W == 256 && !(flags & B2_FLAG_OPLEVEL) && cluster_grid_clusters(P) != 0;
+}
+constexpr bool kClusterBwd = false;   // fused 256x256 adjoint (shoot_cluster_bwd_kernel)
+static bool cluster_bwd_size(int64_t H, int64_t W, int64_t P, int flags) { return kClusterBwd && cluster_size(H, W, P, flags); }
 
 int epdiff_step_big(const float* u, const float* m0, float* unext, float* vout, void* zg, int64_t P, int64_t H,
                     int64_t W, float alpha, float beta, float gamma, float dt, int bg, cudaStream_t st);
@@ -95,8 +102,6 @@ shoot_fwd_kernel(const ShootParams prm) {
   const float sc = (c == 0 || c == W - 1) ? 1.f : 0.5f;
 
   FS::init_luts(twH, twW, csH, csW, tid, NT);
-  if (a.S)
-    for (int i = tid; i < 2 * n_sectors; i += NT) tab_s[i] = a.table[i];
   float* scr_u = prm.scratch + (size_t)blockIdx.x * 2 * prm.field;
   float* scr_m = scr_u + prm.field;
   __syncthreads();
@@ -256,12 +261,14 @@ shoot_fwd_kernel(const ShootParams prm) {
 
     // ---- strain matrix column t of slice b
     if (a.S) {
+      const SectorFrame sf = sector_frame_of(a.table, a.table_slice_stride, a.theta0, a.clockwise, b);
+      for (int i = tid; i < 2 * n_sectors; i += NT) tab_s[i] = sf.table[i];      // this slice's (rotated) boundaries
       for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0ull; cnts_s[i] = 0; }
       __syncthreads();
       const float* tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N
                                              : a.tar + (size_t)p * N;
       strain_bin_frame<NT>(ucur, ucur + N, tarp, reinterpret_cast<const long long*>(a.moments) + 3 * b,
-                           tab_s, n_sectors, H, W, sums_s, cnts_s, tid);
+                           tab_s, n_sectors, H, W, sums_s, cnts_s, tid, sf.theta0, sf.flip);
       strain_store_column<NT>(sums_s, cnts_s, a.S, a.counts, (int)b, t, (int)a.T1, n_sectors, a.n_frames, tid);
     }
     __syncthreads();   // z and bins free for the next pair
@@ -300,17 +307,9 @@ static int sm_count() {
   return sms;
 }
 
-// threads per CTA of the 128x128 kernel (tuning knob; B2_SHOOT_NT=512|1024 overrides for A/B runs)
-static int nt128() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("B2_SHOOT_NT");
-    v = (e && atoi(e) == 512) ? 512 : 1024;   // 1024 measured 22 % faster (profiles/r01_b)
-  }
-  return v;
+static bool fused_size(int64_t H, int64_t W, int flags) {
+  return H == W && (H == 16 || H == 32 || H == 64 || H == 128) && !(flags & B2_FLAG_OPLEVEL);
 }
-
-static bool fused_size(int64_t H, int64_t W) { return H == W && (H == 16 || H == 32 || H == 64 || H == 128); }
 
 static int64_t fused_grid(int64_t P, int64_t H) {
   int per = 1;
@@ -318,7 +317,7 @@ static int64_t fused_grid(int64_t P, int64_t H) {
     case 16: per = FusedCfg<16, 16, 128>::ctas_per_sm(); break;
     case 32: per = FusedCfg<32, 32, 256>::ctas_per_sm(); break;
     case 64: per = FusedCfg<64, 64, 256>::ctas_per_sm(); break;
-    case 128: per = nt128() == 1024 ? FusedCfg<128, 128, 1024>::ctas_per_sm() : FusedCfg<128, 128, 512>::ctas_per_sm(); break;
+    case 128: per = FusedCfg<128, 128, 1024>::ctas_per_sm(); break;   // 1024 threads measured 22 % faster than 512
   }
   int64_t g = (int64_t)sm_count() * per;
   return g < P ? g : P;
@@ -384,8 +383,12 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
   constexpr int LD = FS::LD, N = H * W, RB = NT / W, NB = H / RB;
   float2 *z, *twH, *twW, *csH, *csW;
   FS::carve(smem_raw, z, twH, twW, csH, csW);
-  const int tid = threadIdx.x;
-  const int c = tid % W, br = tid / W;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // Thread <-> pixel map of the adjoint: a thread keeps one column c and walks the NB CONSECUTIVE rows
+  // rbase + k (the forward kernel strides rows by RB instead), lanes along the contiguous axis.  The 2x2 splat
+  // footprints of vertically adjacent pixels then overlap inside one thread and those of horizontally adjacent
+  // pixels inside one warp: splat2_agg merges them before anything goes to the L2 atomic unit.
+  const int c = tid % W, rbase = (tid / W) * NB;
   const int S = prm.num_steps;
   const float mdt = -prm.T / (float)S;
   const FluidParams fp{prm.alpha, prm.beta, prm.gamma, 1.0f / (float)N};
@@ -405,7 +408,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
     float* Gcur = Ga;
     float* Gnext = Gb;
     for (int k = 0; k < NB; ++k) {
-      const int i = (k * RB + br) * W + c;
+      const int i = (rbase + k) * W + c;
       Gcur[i] = prm.gu ? __ldg(prm.gu + (size_t)p * prm.field + i) : 0.f;
       Gcur[N + i] = prm.gu ? __ldg(prm.gu + (size_t)p * prm.field + N + i) : 0.f;
       A[i] = prm.gm0 ? __ldg(prm.gm0 + (size_t)p * prm.field + i) : 0.f;
@@ -419,14 +422,15 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       if (s > 0) {
         // ---- adjoint of u_{s+1} = interp(u_s, v_s, -dt) - dt v_s : dL/dv_s -> z, splat of dL/du_{s+1} -> Gnext
         for (int k = 0; k < NB; ++k) {
-          const int i = (k * RB + br) * W + c;
+          const int i = (rbase + k) * W + c;
           Gnext[i] = 0.f;
           Gnext[N + i] = 0.f;
         }
         __syncthreads();
+        SplatCarry cy{-1, 0.f, 0.f};
 #pragma unroll (kBwdUnrollB1)
         for (int k = 0; k < NB; ++k) {
-          const int r = k * RB + br, i = r * W + c;
+          const int r = rbase + k, i = r * W + c;
           const float g0 = __ldcg(Gcur + i), g1 = __ldcg(Gcur + N + i);
           const float v0 = __ldg(vs + i), v1 = __ldg(vs + N + i);
           const Taps t = make_taps<BG>((float)r + mdt * v0, (float)c + mdt * v1, H, W);
@@ -434,19 +438,14 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           tap_grad<BG>(t, __ldg(us + t.o00), __ldg(us + t.o10), __ldg(us + t.o01), __ldg(us + t.o11), a0, a1);
           tap_grad<BG>(t, __ldg(us + N + t.o00), __ldg(us + N + t.o10), __ldg(us + N + t.o01), __ldg(us + N + t.o11), b0, b1);
           z[r * LD + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
-          const float oma = 1.f - t.a, omb = 1.f - t.b;
-          float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
-          if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
-          atomicAdd(Gnext + t.o00, w00 * g0); atomicAdd(Gnext + t.o01, w01 * g0);
-          atomicAdd(Gnext + t.o10, w10 * g0); atomicAdd(Gnext + t.o11, w11 * g0);
-          atomicAdd(Gnext + N + t.o00, w00 * g1); atomicAdd(Gnext + N + t.o01, w01 * g1);
-          atomicAdd(Gnext + N + t.o10, w10 * g1); atomicAdd(Gnext + N + t.o11, w11 * g1);
+          splat2_agg<BG>(Gnext, N, t, g0, g1, cy, lane);
         }
+        splat_flush(Gnext, N, cy);
       } else {
         // u_0 = 0: u_1 = -dt v_0, so dL/dv_0 = -dt dL/du_1 (+ the direct gradient of the velocity output)
         const float* gv = prm.gvel ? prm.gvel + (size_t)p * prm.field : nullptr;
         for (int k = 0; k < NB; ++k) {
-          const int r = k * RB + br, i = r * W + c;
+          const int r = rbase + k, i = r * W + c;
           float a = mdt * __ldcg(Gcur + i), b = mdt * __ldcg(Gcur + N + i);
           if (gv) { a += __ldg(gv + i); b += __ldg(gv + N + i); }
           z[r * LD + c] = make_float2(a, b);
@@ -462,16 +461,20 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
         float* Wb = Gcur;
 #pragma unroll (kBwdUnrollB3a)
         for (int k = 0; k < NB; ++k) {
-          const int r = k * RB + br, i = r * W + c;
+          const int r = rbase + k, i = r * W + c;
           const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
           Wb[i] = tap_sample<BG>(t, __ldg(m0p + t.o00), __ldg(m0p + t.o10), __ldg(m0p + t.o01), __ldg(m0p + t.o11));
           Wb[N + i] = tap_sample<BG>(t, __ldg(m0p + N + t.o00), __ldg(m0p + N + t.o10), __ldg(m0p + N + t.o01),
                                      __ldg(m0p + N + t.o11));
         }
         __syncthreads();
+        SplatCarry cy{-1, 0.f, 0.f};
 #pragma unroll (kBwdUnrollB3b)
         for (int k = 0; k < NB; ++k) {
-          const int r = k * RB + br, i = r * W + c;
+          const int r = rbase + k, i = r * W + c;
+          // the compose adjoint's REDs into Gnext completed before the barriers above: the own-pixel part of
+          // dL/du_s is a plain read-modify-write (L2 path on both sides), no atomic
+          const float gn0 = __ldcg(Gnext + i), gn1 = __ldcg(Gnext + N + i);
           const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
           const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
           const float sr = diff_scale(r, H);
@@ -481,13 +484,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           const float gw0 = g.x + (d00 * g.x + d01 * g.y);
           const float gw1 = g.y + (d10 * g.x + d11 * g.y);
           const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
-          const float oma = 1.f - t.a, omb = 1.f - t.b;
-          float w00 = oma * omb, w01 = oma * t.b, w10 = t.a * omb, w11 = t.a * t.b;
-          if (BG == B2_BG_ZERO) { w00 *= t.m00; w01 *= t.m01; w10 *= t.m10; w11 *= t.m11; }
-          atomicAdd(A + t.o00, w00 * gw0); atomicAdd(A + t.o01, w01 * gw0);
-          atomicAdd(A + t.o10, w10 * gw0); atomicAdd(A + t.o11, w11 * gw0);
-          atomicAdd(A + N + t.o00, w00 * gw1); atomicAdd(A + N + t.o01, w01 * gw1);
-          atomicAdd(A + N + t.o10, w10 * gw1); atomicAdd(A + N + t.o11, w11 * gw1);
+          splat2_agg<BG>(A, N, t, gw0, gw1, cy, lane);
           float a0, a1, b0, b1;
           tap_grad<BG>(t, __ldg(m0p + t.o00), __ldg(m0p + t.o10), __ldg(m0p + t.o01), __ldg(m0p + t.o11), a0, a1);
           tap_grad<BG>(t, __ldg(m0p + N + t.o00), __ldg(m0p + N + t.o10), __ldg(m0p + N + t.o01),
@@ -503,34 +500,32 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
               + (cmc * (gl_ * Wb[olf]) + c0c * (g.y * w0c) - cpc * (gr_ * Wb[ort]));
           o1 += (cmr * (gu_ * Wb[N + oup]) + c0r * (g.x * w1c) - cpr * (gd_ * Wb[N + odn]))
               + (cmc * (gl_ * Wb[N + olf]) + c0c * (g.y * w1c) - cpc * (gr_ * Wb[N + ort]));
-          atomicAdd(Gnext + i, o0);       // own pixel; atomics keep every access to G on the L2 path
-          atomicAdd(Gnext + N + i, o1);
+          __stcg(Gnext + i, gn0 + o0);
+          __stcg(Gnext + N + i, gn1 + o1);
         }
+        splat_flush(A, N, cy);
         float* tmp = Gcur; Gcur = Gnext; Gnext = tmp;
       } else {
-        // m_0 = Ad*_0 m0 = m0 exactly
+        // m_0 = Ad*_0 m0 = m0 exactly: dL/dm0 = accumulated splats + dL/dm_0, summed in place in shared memory
+        // (the REDs into A completed before the barriers above)
         for (int k = 0; k < NB; ++k) {
-          const int r = k * RB + br, i = r * W + c;
-          const float2 g = z[r * LD + c];
-          atomicAdd(A + i, g.x);
-          atomicAdd(A + N + i, g.y);
+          const int r = rbase + k, i = r * W + c;
+          float2 g = z[r * LD + c];
+          g.x += __ldcg(A + i);
+          g.y += __ldcg(A + N + i);
+          z[r * LD + c] = g;
         }
       }
       __syncthreads();
     }
     // ---- dL/dv0 = flat(dL/dm0)  (or dL/dm0 itself when the forward input was the momentum)
-    for (int k = 0; k < NB; ++k) {
-      const int r = k * RB + br, i = r * W + c;
-      z[r * LD + c] = make_float2(__ldcg(A + i), __ldcg(A + N + i));
-    }
-    __syncthreads();
     if (!prm.v0_is_momentum) fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
     float* out = prm.gv0 + (size_t)p * prm.field;
     // d<sharp(m0), m0>/dm0 = 2 vel and flat(2 vel) = 2 m0: the regularisation gradient needs no transform
     const float g2 = prm.g_reg ? 2.f * __ldg(prm.g_reg + p) : 0.f;
     const float* radd = prm.v0_is_momentum ? prm.traj + ((size_t)P + p) * prm.field : m0p;   // v_0 of the trajectory
     for (int k = 0; k < NB; ++k) {
-      const int r = k * RB + br, i = r * W + c;
+      const int r = rbase + k, i = r * W + c;
       float2 v = z[r * LD + c];
       if (prm.g_reg) { v.x += g2 * __ldg(radd + i); v.y += g2 * __ldg(radd + N + i); }
       out[i] = v.x;
@@ -540,14 +535,43 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
   }
 }
 
+// Resident CTAs per SM of the adjoint kernel as the runtime reports it; the per-CTA scratch is sized from it.
+template <int H, int W, int NT>
+static int bwd_ctas_per_sm() {
+  static int cached = 0;
+  if (cached) return cached;
+  const size_t smem = FluidSmem<H, W>::bytes;
+  int per = 0;
+  if (cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, NT, smem) != cudaSuccess ||
+      per < 1) {
+    (void)cudaGetLastError();   // no device / query failed: shared-memory bound (not cached)
+    per = (int)((224 * 1024) / (smem + 1024));
+    if (per < 1) per = 1;
+    if (per * NT > 2048) per = 2048 / NT;
+    return per;
+  }
+  cached = per;
+  return per;
+}
+
+static int64_t fused_bwd_grid(int64_t P, int64_t H) {
+  int per = 1;
+  switch ((int)H) {
+    case 16: per = bwd_ctas_per_sm<16, 16, 128>(); break;
+    case 32: per = bwd_ctas_per_sm<32, 32, 256>(); break;
+    case 64: per = bwd_ctas_per_sm<64, 64, 256>(); break;
+    case 128: per = bwd_ctas_per_sm<128, 128, 1024>(); break;
+  }
+  const int64_t g = (int64_t)sm_count() * per;
+  return g < P ? g : P;
+}
+
 template <int H, int W, int NT>
 static int launch_fused_bwd(const ShootBwdParams& prm, int background, cudaStream_t st) {
   const size_t smem = FluidSmem<H, W>::bytes;
-  int per = (int)((224 * 1024) / (smem + 1024));
-  if (per < 1) per = 1;
-  if (per * NT > 2048) per = 2048 / NT;
-  int64_t grid = (int64_t)sm_count() * per;
-  if (grid > prm.P) grid = prm.P;
+  const int64_t grid = fused_bwd_grid(prm.P, H);
   if (background == B2_BG_CLAMP) {
     B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP><<<(unsigned)grid, NT, smem, st>>>(prm);
@@ -588,10 +612,14 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 using namespace b2;
 
 extern "C" int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps) {
+  return b2_shoot_workspace_bytes_flags(B, T1, H, W, num_steps, 0);
+}
+
+extern "C" int64_t b2_shoot_workspace_bytes_flags(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps, int flags) {
   if (B <= 0 || T1 <= 0 || H <= 0 || W <= 0 || num_steps <= 0) return 0;
   const int64_t P = B * T1, field = 2 * H * W;
-  if (fused_size(H, W)) return (int64_t)align256(sizeof(float) * (size_t)fused_grid(P, H) * 2 * field);
-  if (cluster_size(H, W)) return (int64_t)align256((size_t)cluster_workspace_bytes(P));
+  if (fused_size(H, W, flags)) return (int64_t)align256(sizeof(float) * (size_t)fused_grid(P, H) * 2 * field);
+  if (cluster_size(H, W, P, flags)) return (int64_t)align256((size_t)cluster_workspace_bytes(P));
   // path B: m0 (if not given) + u scratch + m/v buffer + FFT scratch
   return (int64_t)(3 * align256(sizeof(float) * (size_t)P * field) + align256((size_t)b2_fluid_workspace_bytes(P, H, W)));
 }
@@ -609,12 +637,13 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   if (a.S && (a.n_sectors < 3 || a.n_sectors > kFusedMaxSectors || a.n_frames < 1)) return B2_E_PARAM;
   const int64_t P = a.B * a.T1, H = a.H, W = a.W, field = 2 * H * W;
   if (P > ((int64_t)1 << 30)) return B2_E_SHAPE;
-  const int64_t need = b2_shoot_workspace_bytes(a.B, a.T1, H, W, a.num_steps);
+  if (a.table_slice_stride < 0 || (a.flags & ~B2_FLAG_OPLEVEL)) return B2_E_PARAM;
+  const int64_t need = b2_shoot_workspace_bytes_flags(a.B, a.T1, H, W, a.num_steps, a.flags);
   if (need <= 0) return B2_E_FFTSIZE;
   if (!workspace || workspace_bytes < need) return B2_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (fused_size(H, W)) {
+  if (fused_size(H, W, a.flags)) {
     ShootParams prm;
     prm.a = a;
     prm.scratch = reinterpret_cast<float*>(workspace);
@@ -625,13 +654,12 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
       case 16: return launch_fused<16, 16, 128>(prm, grid, st);
       case 32: return launch_fused<32, 32, 256>(prm, grid, st);
       case 64: return launch_fused<64, 64, 256>(prm, grid, st);
-      case 128: return nt128() == 1024 ? launch_fused<128, 128, 1024>(prm, grid, st)
-                                       : launch_fused<128, 128, 512>(prm, grid, st);
+      case 128: return launch_fused<128, 128, 1024>(prm, grid, st);
     }
     return B2_E_FFTSIZE;
   }
 
-  if (cluster_size(H, W)) {
+  if (cluster_size(H, W, P, a.flags)) {
     if (a.S && (a.n_sectors > kMaxSectors)) return B2_E_PARAM;
     return launch_shoot_cluster(a, workspace, st);
   }
@@ -681,8 +709,9 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
     }
   }
   if (a.S) {
-    if (int e = b2_strain_sector_fwd(a.u, a.tar, a.moments, a.table, a.S, a.counts, a.B, a.T1, H, W, a.n_sectors,
-                                     a.n_frames, stream))
+    const b2_sector_frame fr{a.table, a.table_slice_stride, a.theta0, a.clockwise};
+    if (int e = b2_strain_sector_fwd_ex(a.u, a.tar, a.moments, &fr, a.S, a.counts, a.B, a.T1, H, W, a.n_sectors,
+                                        a.n_frames, stream))
       return e;
   }
   if (a.loss_terms) {
@@ -693,9 +722,18 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
 
 extern "C" int64_t b2_sizeof_shoot_args(void) { return (int64_t)sizeof(b2_shoot_args); }
 
+extern "C" int64_t b2_sizeof_shoot_bwd_args(void) { return (int64_t)sizeof(b2_shoot_bwd_args); }
+
 extern "C" int64_t b2_shoot_bwd_workspace_bytes(int64_t P, int64_t H, int64_t W) {
+  return b2_shoot_bwd_workspace_bytes_flags(P, H, W, 0);
+}
+
+// sized per path: resident CTAs (clusters) x 3 fields for the fused adjoints, 5 P fields + FFT scratch op-level
+extern "C" int64_t b2_shoot_bwd_workspace_bytes_flags(int64_t P, int64_t H, int64_t W, int flags) {
   if (P <= 0 || H <= 0 || W <= 0) return 0;
-  const int64_t fw = b2_fluid_workspace_bytes(P, H, W);
+  if (fused_size(H, W, flags)) return (int64_t)align256(sizeof(float) * (size_t)fused_bwd_grid(P, H) * 3 * 2 * H * W);
+  if (cluster_bwd_size(H, W, P, flags)) return (int64_t)align256((size_t)cluster_bwd_workspace_bytes(P));
+  const int64_t fw = b2_fluid_workspace_bytes(P, H, W);   // 0 for grids whose FFT runs in shared memory
   return (int64_t)(5 * align256(sizeof(float) * (size_t)P * 2 * H * W) + align256((size_t)fw));
 }
 
@@ -711,13 +749,28 @@ extern "C" int b2_shoot_bwd_loss(const float* gu, const float* gvel, const float
                                  const float* m0, const float* traj, float* gv0, int64_t P, int64_t H, int64_t W,
                                  int num_steps, float alpha, float beta, float gamma, float T, int background,
                                  int v0_is_momentum, void* workspace, int64_t workspace_bytes, void* stream) {
+  const b2_shoot_bwd_args a{gu, gvel, gm0, g_reg, m0, traj, gv0, P, H, W, num_steps, background, v0_is_momentum, 0,
+                            alpha, beta, gamma, T};
+  return b2_shoot_bwd_ex(&a, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b2_shoot_bwd_ex(const b2_shoot_bwd_args* args, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!args) return B2_E_NULL;
+  const float *gu = args->gu, *gvel = args->gvel, *gm0 = args->gm0, *g_reg = args->g_reg, *m0 = args->m0, *traj = args->traj;
+  float* gv0 = args->gv0;
+  const int64_t P = args->P, H = args->H, W = args->W;
+  const int num_steps = args->num_steps, background = args->background, v0_is_momentum = args->v0_is_momentum;
+  const float alpha = args->alpha, beta = args->beta, gamma = args->gamma, T = args->T;
   if (!m0 || !traj || !gv0) return B2_E_NULL;
   if (P <= 0 || H < 2 || W < 2 || P > ((int64_t)1 << 30)) return B2_E_SHAPE;
-  if (num_steps < 1 || !(gamma > 0.f) || !(T > 0.f)) return B2_E_PARAM;
-  if (!workspace || workspace_bytes < b2_shoot_bwd_workspace_bytes(P, H, W)) return B2_E_WORKSPACE;
+  if (num_steps < 1 || !(gamma > 0.f) || !(T > 0.f) || (args->flags & ~B2_FLAG_OPLEVEL)) return B2_E_PARAM;
+  if (background != B2_BG_CLAMP && background != B2_BG_ZERO) return B2_E_PARAM;
+  const int64_t need = b2_shoot_bwd_workspace_bytes_flags(P, H, W, args->flags);
+  if (need <= 0) return B2_E_FFTSIZE;
+  if (!workspace || workspace_bytes < need) return B2_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (fused_size(H, W) && !getenv("B2_BWD_OPLEVEL")) {
-    // path A: one persistent kernel; scratch = (resident CTAs) x 3 fields <= 5 P fields of the op-level layout
+  if (fused_size(H, W, args->flags) || cluster_bwd_size(H, W, P, args->flags)) {
+    // fused adjoint: one persistent kernel; scratch = resident CTAs (clusters) x 3 fields
     ShootBwdParams prm{gu, gvel, gm0, g_reg, m0, traj, gv0, reinterpret_cast<float*>(workspace), P, 2 * H * W,
                        num_steps, v0_is_momentum, alpha, beta, gamma, T};
     switch ((int)H) {
@@ -725,6 +778,7 @@ extern "C" int b2_shoot_bwd_loss(const float* gu, const float* gvel, const float
       case 32: return launch_fused_bwd<32, 32, 256>(prm, background, st);
       case 64: return launch_fused_bwd<64, 64, 256>(prm, background, st);
       case 128: return launch_fused_bwd<128, 128, 1024>(prm, background, st);
+      case 256: return launch_shoot_cluster_bwd(prm, background, st);
     }
   }
   const size_t n = (size_t)P * 2 * H * W, fbytes = align256(sizeof(float) * n);

@@ -24,6 +24,8 @@ constexpr int kCN = kCH * kCW;
 
 __constant__ int c_group_block[4][4] = {{0, 8, 1, 15}, {2, 14, 3, 13}, {4, 12, 5, 11}, {6, 10, 7, 9}};
 
+struct ShootBwdParams;
+
 struct ClusterParams {
   b2_shoot_args a;
   float* scratch;        // per cluster: [u ping | u pong | m0] + bins; the spectrum exchange reuses the next-u field
@@ -265,6 +267,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         for (int i = tid; i < ns; i += kCNT) { bins[i] = 0ull; cnts[i] = 0u; }
       cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
       const long long* mom = reinterpret_cast<const long long*>(a.moments) + 3 * b;
+      const SectorFrame sf = sector_frame_of(a.table, a.table_slice_stride, a.theta0, a.clockwise, b);
       const long long cnt = mom[0], sx = mom[1], sy = mom[2];
       float c0, c1;
       centroid_from_moments(mom, H, W, c0, c1);
@@ -275,7 +278,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
         if (!(tarp[i] > 0.5f)) continue;
-        const int ksec = classify_sector(cnt * r - sx, cnt * c - sy, a.table, ns);
+        const int ksec = classify_sector(cnt * r - sx, cnt * c - sy, sf.table, ns, sf.theta0, sf.flip);
         if (ksec < 0) continue;
         int rlo, rhi, clo, chi; float sr, sc;
         diff_idx(r, H, rlo, rhi, sr);
@@ -381,5 +384,9 @@ int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t s
 #undef B2_CLUSTER_LAUNCH
   return B2_OK;
 }
+
+// fused 256x256 adjoint: not built yet (shoot.cu: kClusterBwd)
+int64_t cluster_bwd_workspace_bytes(int64_t) { return 0; }
+int launch_shoot_cluster_bwd(const ShootBwdParams&, int, cudaStream_t) { return B2_E_FFTSIZE; }
 
 }  // namespace b2

@@ -26,7 +26,8 @@ __device__ __forceinline__ float fixed_to_mean(unsigned long long s, int cnt) {
 template <int NT>
 __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u1, const float* __restrict__ mask,
                                                  const long long* mom, const int32_t* tab_s, int n_sectors,
-                                                 int H, int W, unsigned long long* sums_s, int* cnts_s, int tid) {
+                                                 int H, int W, unsigned long long* sums_s, int* cnts_s, int tid,
+                                                 float theta0 = 0.f, bool flip = false) {
   const long long cnt = mom[0], sx = mom[1], sy = mom[2];
   float c0, c1;
   centroid_from_moments(mom, H, W, c0, c1);
@@ -34,7 +35,7 @@ __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u
   for (int x = tid; x < N; x += NT) {
     if (!(mask[x] > 0.5f)) continue;
     const int r = x / W, c = x - r * W;
-    const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors);
+    const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors, theta0, flip);
     if (k < 0) continue;
     int rlo, rhi, clo, chi; float sr, sc;
     diff_idx(r, H, rlo, rhi, sr);

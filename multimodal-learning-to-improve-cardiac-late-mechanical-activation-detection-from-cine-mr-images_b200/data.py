@@ -55,6 +55,40 @@ def align_n_frames_to(volume, n_target_frames, frame_idx=-1, padding_method="edg
     return np.pad(volume, widths, mode=padding_method)
 
 
+class _RegroupPairs(torch.autograd.Function):
+    """(P,C,H,W) per-pair fields -> (n_slices,C,F,H,W) by slot table; differentiable like the reference's
+    stack / permute / pad (the joint trainer backpropagates the LMA loss through it,
+    /root/reference/modules/trainer/joint_registration_regression_trainer.py:290-320)."""
+
+    @staticmethod
+    def forward(ctx, u, slot_d, n_slices, F):
+        from . import _lib
+        from ._lib import check, lib, ptr, stream
+        P, C, H, W = u.shape
+        with _lib.on_device(u):
+            out = torch.empty((n_slices, C, F, H, W), dtype=u.dtype, device=u.device)
+            check(lib().b2_regroup_pairs(ptr(u), ptr(slot_d), ptr(out), P, n_slices, F, C, H, W, stream()),
+                  "b2_regroup_pairs")
+        _lib.count_launch()
+        ctx.save_for_backward(slot_d)
+        ctx.dims = (P, C, H, W, n_slices, F)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import _lib
+        from ._lib import check, lib, ptr, stream
+        (slot_d,) = ctx.saved_tensors
+        P, C, H, W, n_slices, F = ctx.dims
+        gout = gout.contiguous()
+        with _lib.on_device(gout):
+            gu = torch.empty((P, C, H, W), dtype=gout.dtype, device=gout.device)
+            check(lib().b2_regroup_pairs_bwd(ptr(gout), ptr(slot_d), ptr(gu), P, n_slices, F, C, H, W, stream()),
+                  "b2_regroup_pairs_bwd")
+        _lib.count_launch()
+        return gu, None, None, None
+
+
 def merge_data_of_same_slice_from_batch(batch, reg_pred_dict, n_frames_to_use_for_regression, used_device):
     """Regroup the per-pair outputs of a batch by slice.
 
@@ -65,7 +99,7 @@ def merge_data_of_same_slice_from_batch(batch, reg_pred_dict, n_frames_to_use_fo
     ``set``, i.e. in arbitrary order; ``'batch_slice_full_ids'`` names the order used).
     """
     from . import _lib
-    from ._lib import check, lib, ptr, require_cuda, stream
+    from ._lib import require_cuda
     ids = list(batch["slice_full_id"])
     u = reg_pred_dict["displacement"].contiguous()
     require_cuda(u)
@@ -83,9 +117,7 @@ def merge_data_of_same_slice_from_batch(batch, reg_pred_dict, n_frames_to_use_fo
         slot.append(s * F + pos if pos < F else -1)
         seen[sid][1] = pos + 1
     slot_d = torch.tensor(slot, dtype=torch.int32).to(u.device)
-    out = torch.empty((len(order), C, F, H, W), dtype=u.dtype, device=u.device)
-    check(lib().b2_regroup_pairs(ptr(u), ptr(slot_d), ptr(out), P, len(order), F, C, H, W, stream()), "b2_regroup_pairs")
-    _lib.count_launch()
+    out = _RegroupPairs.apply(u, slot_d, len(order), F)      # keeps the graph: the LMA loss reaches the registration net
     first_t = torch.tensor(first)
     return {
         "pred_displacement_fields": out,

@@ -61,15 +61,28 @@ class VelocityNet(nn.Module):
         return self._up2(v, x.shape[-2:]).contiguous()
 
 
-def svd_smooth(S: torch.Tensor, rank: int) -> torch.Tensor:
+def svd_smooth(S: torch.Tensor, rank: int, grad: str = "projection") -> torch.Tensor:
     """Rank truncation of each (sectors x frames) strain matrix.
 
-    Same operation as ``SVDDenoise`` (/root/reference/modules/data/utils/DENSE_utils.py:11-14),
-    selected by ``strainmat_smoothing_method: "SVD"`` (configs/config.json:113-114).
+    Same operation as ``SVDDenoise`` (/root/reference/modules/data/utils/DENSE_utils.py:11-14: ``u @ diag(s[:rank]) @
+    vh``), selected by ``strainmat_smoothing_method: "SVD"`` (configs/config.json:113-114); checked against the
+    reference function's own output (tests/golden/ref_sectors.npz).
+
+    The reference applies it to numpy ground truth, so it defines no gradient.  Two explicit choices here:
+
+    * ``grad="projection"`` (default, intended): the left basis ``U_r`` is treated as a constant, the backward is
+      ``g -> U_r U_r^T g``, the orthogonal projection onto the retained subspace.  It is defined for every input -
+      the strain matrix is edge-padded beyond the cine frames, hence rank deficient with repeated zero singular
+      values, where the derivative of the SVD itself does not exist (NaN in ``torch.linalg.svd`` backward).
+    * ``grad="exact"``: differentiate through ``torch.linalg.svd`` (the true derivative of the truncation; needs
+      distinct singular values).
     """
-    # U_r U_r^T S equals the rank-r truncation U_r diag(s_r) V_r^T.  The basis is detached: the strain
-    # matrix is edge-padded beyond the cine frames, hence rank deficient with repeated zero singular
-    # values, where the derivative of the SVD itself is undefined (NaN in torch.linalg.svd backward).
+    if grad == "exact":
+        U, s, Vh = torch.linalg.svd(S, full_matrices=False)
+        return (U[..., :rank] * s[..., None, :rank]) @ Vh[..., :rank, :]
+    if grad != "projection":
+        raise ValueError(f"grad must be 'projection' or 'exact', got {grad!r}")
+    # U_r U_r^T S equals the rank-r truncation U_r diag(s_r) V_r^T
     with torch.no_grad():
         U = torch.linalg.svd(S, full_matrices=False)[0][..., :rank]
     return U @ (U.transpose(-1, -2) @ S)
@@ -87,6 +100,7 @@ class JointRegisterStrainMatNet(nn.Module):
         self.sigma = float(config.get("sigma", 0.03))
         self.smoothing = config.get("strainmat_smoothing_method", None)
         self.smoothing_rank = int(config.get("strainmat_smoothing_SVD_rank", 5))
+        self.smoothing_grad = config.get("strainmat_smoothing_grad", "projection")       # see svd_smooth
         self.fused_loss_terms = bool(config.get("fused_loss_terms", False))   # adds 'registration_loss_terms'
         self.metric = FluidMetric(config.get("fluid_params", (1.0, 0.1, 0.05)))
         self.velocity_net = VelocityNet(int(config.get("velocity_net_width", 16)),
@@ -97,17 +111,18 @@ class JointRegisterStrainMatNet(nn.Module):
         v0 = self.velocity_net(src, tar).float()      # the path is fp32 even when the net runs under autocast
         return shoot_warp_pairs(v0, src, tar, self.metric, self.num_steps, loss_terms=self.fused_loss_terms)
 
-    def forward_volume(self, src_vol, tar_vol):
-        """src_vol, tar_vol (B,1,T-1,H,W) -> {'strain_matrix','deformed_source','velocity','momentum',...}."""
+    def forward_volume(self, src_vol, tar_vol, theta0=None, clockwise=None):
+        """src_vol, tar_vol (B,1,T-1,H,W) -> {'strain_matrix','deformed_source','velocity','momentum',...}.
+        ``theta0`` / ``clockwise``: optional per-slice sector frame of the strain-matrix rows (strain.py)."""
         B, C, T1, H, W = tar_vol.shape
         # pair (b, t) registers src_vol[b, :, t] to tar_vol[b, :, t]: frame 0 for every t under the Lagrangian
         # split, frame t under the Eulerian one (modules/data/__init__.py:108-113)
         v0 = self.velocity_net(src_vol.reshape(B * T1, C, H, W), tar_vol.reshape(B * T1, C, H, W)).float()   # path is fp32
         out = shoot_warp_strain(v0, src_vol, tar_vol, self.metric, self.num_steps,
                                 n_sectors=self.n_sectors, n_frames=self.n_strain_matrix_frames,
-                                loss_terms=self.fused_loss_terms)
+                                loss_terms=self.fused_loss_terms, theta0=theta0, clockwise=clockwise)
         if self.smoothing == "SVD":
-            out["strain_matrix"] = svd_smooth(out["strain_matrix"], self.smoothing_rank)
+            out["strain_matrix"] = svd_smooth(out["strain_matrix"], self.smoothing_rank, self.smoothing_grad)
         return out
 
 

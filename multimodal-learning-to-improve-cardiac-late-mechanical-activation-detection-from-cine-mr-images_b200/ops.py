@@ -29,6 +29,7 @@ def _bcast_dims(I, u):
 
 class InterpFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, I, u, dt, background):
         I = I.contiguous()
         u = u.contiguous()
@@ -45,6 +46,7 @@ class InterpFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gout):
         I, u = ctx.saved_tensors
         gout = gout.contiguous()
@@ -65,6 +67,7 @@ def interp(I, u, dt=1.0, background="clamp"):
 
 class SplatFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, J, u, dt, background, need_weights):
         J = J.contiguous()
         u = u.contiguous()
@@ -85,6 +88,7 @@ class SplatFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gout, gw=None):
         J, u = ctx.saved_tensors
         gout = gout.contiguous()
@@ -122,6 +126,7 @@ def _field_dims(*ts):
 
 class ComposeFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, u, v, dt, background):
         u = u.contiguous()
         v = v.contiguous()
@@ -137,6 +142,7 @@ class ComposeFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gout):
         u, v = ctx.saved_tensors
         gout = gout.contiguous()
@@ -156,6 +162,7 @@ def compose_disp_vel(u, v, dt=1.0, background="clamp"):
 
 class JTVFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, v, w, displacement, transpose):
         v = v.contiguous()
         w = w.contiguous()
@@ -171,6 +178,7 @@ class JTVFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gout):
         v, w = ctx.saved_tensors
         gout = gout.contiguous()
@@ -190,6 +198,7 @@ def jacobian_times_vectorfield(v, w, displacement=True, transpose=False):
 
 class AdStarFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, u, m, background):
         u = u.contiguous()
         m = m.contiguous()
@@ -204,6 +213,7 @@ class AdStarFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gout):
         u, m = ctx.saved_tensors
         gout = gout.contiguous()
@@ -226,6 +236,7 @@ class FluidFunction(torch.autograd.Function):
     """flat / sharp.  Self-adjoint: the backward is the same operator on the gradient."""
 
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, f, alpha, beta, gamma, inverse):
         f = f.contiguous()
         require_cuda(f)
@@ -236,6 +247,7 @@ class FluidFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gout):
         return fluid_apply(gout.contiguous(), *ctx.params), None, None, None, None
 

@@ -59,6 +59,76 @@ def allreduce_gradients(params, world_size: int | None = None, bucket_bytes: int
     return n_coll
 
 
+class GradientAllReducer:
+    """Gradient all-reduce overlapped with the rest of the backward pass.
+
+    ``buckets``: lists of parameters in the order their gradients become ready during ``backward()`` (for the joint
+    training step: the LMA net first, the registration net last).  A post-accumulate-grad hook counts the ready
+    gradients of each bucket; when a bucket is complete its gradients are flattened and ONE asynchronous
+    all-reduce is launched at once - NCCL runs it on its own stream, so the LMA bucket travels while the EPDiff
+    adjoint kernel is still running.  ``finish()`` (after ``backward()``) waits for the collectives, averages and
+    scatters the results back into ``.grad``; it also launches any bucket whose hooks did not all fire (parameters
+    without gradient).  Without an initialised process group (or world size 1) everything is a no-op.
+    """
+
+    def __init__(self, buckets):
+        self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
+        self.buckets = [b for b in self.buckets if b]
+        self._ready = [0] * len(self.buckets)
+        self._pending = [None] * len(self.buckets)
+        self._hooks = []
+        for bi, b in enumerate(self.buckets):
+            for p in b:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _make_hook(self, bi):
+        def hook(_param):
+            self._ready[bi] += 1
+            if self._ready[bi] == len(self.buckets[bi]):
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        if self._pending[bi] is not None or not self._active():
+            return
+        grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+        self._pending[bi] = (work, flat, grads)
+
+    def finish(self) -> int:
+        """Wait for the launched buckets (launching the incomplete ones first); returns the number of collectives."""
+        n = 0
+        if self._active():
+            ws = dist.get_world_size()
+            for bi in range(len(self.buckets)):
+                self._launch(bi)
+            for bi, pend in enumerate(self._pending):
+                if pend is None:
+                    continue
+                work, flat, grads = pend
+                work.wait()
+                flat.div_(ws)
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                n += 1
+        self._ready = [0] * len(self.buckets)
+        self._pending = [None] * len(self.buckets)
+        return n
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def gather_strain_matrices(S_local: torch.Tensor, n_slices_total: int) -> torch.Tensor | None:
     """Gather the per-rank (B_r,1,K,F) strain matrices on rank 0 in slice order (inference only)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

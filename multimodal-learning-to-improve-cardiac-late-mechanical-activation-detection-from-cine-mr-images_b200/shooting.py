@@ -10,15 +10,33 @@ trajectory (``b2_shoot_bwd``).
 from __future__ import annotations
 
 import ctypes as C
-import time
 
 import torch
 from torch.autograd.function import once_differentiable
 
+import contextlib
+
 from . import _lib
-from ._lib import ShootArgs, check, lib, ptr, require_cuda, stream
+from ._lib import ShootArgs, ShootBwdArgs, check, lib, ptr, require_cuda, stream
 from .ops import BG, Ad_star, FluidMetric, compose_disp_vel
-from .strain import N_SECTORS, mask_moments, sector_table
+from .strain import N_SECTORS, Frame, mask_moments
+
+# Path selection is explicit: these are the B2_FLAG_* words handed to b2_shoot_fwd / b2_shoot_bwd_ex.  The fused
+# kernels are the default wherever they exist; `force_oplevel` selects the op-level kernel sequence (path B) for
+# A/B comparisons and tests.  No environment variable is read.
+_flags = {"fwd": 0, "bwd": 0}
+
+
+@contextlib.contextmanager
+def force_oplevel(fwd: bool = False, bwd: bool = False):
+    """Within the block, run the forward and/or the adjoint as the op-level kernel sequence (B2_FLAG_OPLEVEL)."""
+    old = dict(_flags)
+    _flags["fwd"] = _lib.FLAG_OPLEVEL if fwd else 0
+    _flags["bwd"] = _lib.FLAG_OPLEVEL if bwd else 0
+    try:
+        yield
+    finally:
+        _flags.update(old)
 
 
 def EPDiff_step(metric: FluidMetric, m0, dt, phiinv, mommask=None, background="clamp"):
@@ -53,10 +71,12 @@ def _alloc_outputs(P, B, T1, H, W, dev, want, v0_is_momentum, n_sectors, n_frame
     return out
 
 
-def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background, n_sectors, n_frames,
+def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
                   B, T1, want, v0_is_momentum, src_per_pair, save_traj, out=None, ws=None,
-                  src_slice_stride=0, tar_slice_stride=0):
-    """Run ``b2_shoot_fwd``; outputs are allocated here unless ``out`` (contiguous tensors) is given."""
+                  src_slice_stride=0, tar_slice_stride=0, first_slice=0):
+    """Run ``b2_shoot_fwd``; outputs are allocated here unless ``out`` (contiguous tensors) is given.
+    ``frame``: :class:`strain.Frame` of the batch (``first_slice`` = offset of this launch's slices in it) or None.
+    The caller has made the tensors' device current (``_lib.device_guard`` / ``on_device``)."""
     P, _, H, W = v0.shape
     dev = v0.device
     if out is None:
@@ -65,7 +85,10 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
     a.v0, a.src, a.tar = v0.data_ptr(), (src.data_ptr() if src is not None else None), \
         (tar.data_ptr() if tar is not None else None)
     a.moments = moments.data_ptr() if moments is not None else None
-    a.table = table.data_ptr() if table is not None else None
+    if frame is not None:
+        fs = frame.c_struct(first_slice)
+        a.table, a.table_slice_stride, a.theta0, a.clockwise = fs.table, fs.table_slice_stride, fs.theta0, fs.clockwise
+    a.flags = _flags["fwd"]
     for k in ("m0", "vel", "u", "sdef", "S", "counts", "traj", "loss_terms"):
         setattr(a, k, out[k].data_ptr() if k in out else None)
     a.B, a.T1, a.H, a.W = B, T1, H, W
@@ -73,12 +96,12 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
     a.num_steps, a.src_per_pair, a.v0_is_momentum = int(num_steps), int(src_per_pair), int(v0_is_momentum)
     a.n_sectors, a.n_frames, a.background = int(n_sectors), int(n_frames), int(background)
     a.alpha, a.beta, a.gamma, a.T = metric.alpha, metric.beta, metric.gamma, float(T)
-    nbytes = lib().b2_shoot_workspace_bytes(B, T1, H, W, int(num_steps))
+    nbytes = lib().b2_shoot_workspace_bytes_flags(B, T1, H, W, int(num_steps), a.flags)
     if nbytes <= 0:
         check(-4, "b2_shoot_workspace_bytes")
     if ws is None or ws.numel() < nbytes:
         ws = _workspace(nbytes, dev)
-    check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), nbytes, stream()), "b2_shoot_fwd")
+    check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), ws.numel(), stream()), "b2_shoot_fwd")
     fused = _fused_size(H, W)                        # one persistent kernel (256: one 4-CTA cluster per pair)
     _lib.count_launch(1 if fused else 3 + 3 * int(num_steps) + 2)   # path B: flat, 3 kernels per step, warp, strain
     return out
@@ -87,12 +110,18 @@ def _launch_shoot(v0, src, tar, moments, table, metric, num_steps, T, background
 def _shoot_bwd(gu, gvel, gm0, m0, traj, metric, num_steps, T, background, v0_is_momentum, g_reg=None):
     P, _, H, W = m0.shape
     gv0 = torch.empty_like(m0)
-    nbytes = lib().b2_shoot_bwd_workspace_bytes(P, H, W)
+    a = ShootBwdArgs()
+    for k, t in (("gu", gu), ("gvel", gvel), ("gm0", gm0), ("g_reg", g_reg), ("m0", m0), ("traj", traj), ("gv0", gv0)):
+        setattr(a, k, t.data_ptr() if t is not None else None)
+    a.P, a.H, a.W = P, H, W
+    a.num_steps, a.background, a.v0_is_momentum, a.flags = int(num_steps), int(background), int(v0_is_momentum), _flags["bwd"]
+    a.alpha, a.beta, a.gamma, a.T = metric.alpha, metric.beta, metric.gamma, float(T)
+    nbytes = lib().b2_shoot_bwd_workspace_bytes_flags(P, H, W, a.flags)       # sized per path (fused: resident CTAs)
+    if nbytes <= 0:
+        check(-4, "b2_shoot_bwd_workspace_bytes")
     ws = _workspace(nbytes, m0.device)
-    check(lib().b2_shoot_bwd_loss(ptr(gu), ptr(gvel), ptr(gm0), ptr(g_reg), ptr(m0), ptr(traj), ptr(gv0), P, H, W,
-                                  int(num_steps), metric.alpha, metric.beta, metric.gamma, float(T), int(background),
-                                  int(v0_is_momentum), ptr(ws), nbytes, stream()), "b2_shoot_bwd_loss")
-    _lib.count_launch(6 * int(num_steps) + 1)
+    check(lib().b2_shoot_bwd_ex(C.byref(a), ptr(ws), nbytes, stream()), "b2_shoot_bwd_ex")
+    _lib.count_launch(1 if _fused_bwd_size(H, W) else 6 * int(num_steps) + 1)
     return gv0
 
 
@@ -100,6 +129,7 @@ class ExpmapFunction(torch.autograd.Function):
     """u = expmap(metric, m0): fused forward, adjoint sweep backward."""
 
     @staticmethod
+    @_lib.device_guard
     def forward(ctx, m0, metric, T, num_steps, background):
         m0 = m0.contiguous()
         require_cuda(m0)
@@ -114,6 +144,7 @@ class ExpmapFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gu):
         m0, traj = ctx.saved_tensors
         metric, num_steps, T, background = ctx.cfg
@@ -128,15 +159,22 @@ def expmap(metric: FluidMetric, m0, T=1.0, num_steps=10, phiinv=None, mommask=No
     Returns the inverse-map displacement u with phi^-1(x) = x + u(x).  With the
     default ``phiinv=None, mommask=None`` the whole geodesic is one fused kernel;
     otherwise it is the step-by-step composition of :func:`EPDiff_step`.
-    ``checkpoints`` is accepted for signature compatibility (the fused path stores
-    (u_s, v_s) per step, which is what the adjoint needs).
+    ``checkpoints``: upstream wraps each step in ``torch.utils.checkpoint`` to trade recomputation for memory.
+    The fused path already keeps the minimum the adjoint needs ((u_s, v_s) per step) and recomputes the rest
+    inside the adjoint kernel, so the flag changes nothing there; on the step-by-step path it checkpoints every
+    step exactly like upstream (same values, same gradient).
     """
     if phiinv is None and mommask is None:
         return ExpmapFunction.apply(m0, metric, float(T), int(num_steps), BG[background])
     u = torch.zeros_like(m0) if phiinv is None else phiinv
     dt = T / num_steps
     for _ in range(num_steps):
-        u = EPDiff_step(metric, m0, dt, u, mommask=mommask, background=background)
+        if checkpoints and torch.is_grad_enabled() and (m0.requires_grad or u.requires_grad):
+            from torch.utils.checkpoint import checkpoint
+            u = checkpoint(lambda m, p: EPDiff_step(metric, m, dt, p, mommask=mommask, background=background),
+                           m0, u, use_reentrant=False)
+        else:
+            u = EPDiff_step(metric, m0, dt, u, mommask=mommask, background=background)
     return u
 
 
@@ -148,13 +186,14 @@ class ShootWarpStrainFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, v0, src, tar, moments, table, metric, num_steps, T, background, n_sectors, n_frames, B, T1,
+    @_lib.device_guard
+    def forward(ctx, v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames, B, T1,
                 src_per_pair, with_strain, src_ss, tar_ss, with_loss=False):
         v0 = v0.contiguous()
         require_cuda(v0)
         require_cuda(src if src_ss == 0 else None, tar if tar_ss == 0 else None)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        out = _launch_shoot(v0, src, tar, moments if with_strain else None, table if with_strain else None, metric,
+        out = _launch_shoot(v0, src, tar, moments if with_strain else None, frame if with_strain else None, metric,
                             num_steps, T, background, n_sectors, n_frames, B, T1,
                             {"m0": True, "vel": True, "sdef": True, "S": with_strain, "loss_terms": with_loss}, False,
                             src_per_pair, need, src_slice_stride=src_ss, tar_slice_stride=tar_ss)
@@ -162,8 +201,9 @@ class ShootWarpStrainFunction(torch.autograd.Function):
                    src_ss, tar_ss)
         ctx.set_materialize_grads(False)      # unused outputs arrive as None in backward, not as zero tensors
         if need:
-            ctx.save_for_backward(out["m0"], out["u"], out["traj"], src, tar, moments, table,
+            ctx.save_for_backward(out["m0"], out["u"], out["traj"], src, tar, moments,
                                   out.get("counts", torch.empty(0, device=v0.device)))
+            ctx.frame = frame
         if with_strain:
             S = out["S"]
         else:
@@ -178,8 +218,9 @@ class ShootWarpStrainFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_lib.device_guard
     def backward(ctx, gm0, gvel, gu, gsdef, gS, glt=None):
-        m0, u, traj, src, tar, moments, table, counts = ctx.saved_tensors
+        m0, u, traj, src, tar, moments, counts = ctx.saved_tensors
         metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain, src_ss, tar_ss = ctx.cfg
         P, _, H, W = m0.shape
         want_dsrc = ctx.needs_input_grad[1]
@@ -193,9 +234,10 @@ class ShootWarpStrainFunction(torch.autograd.Function):
             du = torch.empty_like(u)
             tar_c = tar.reshape(B, T1, H, W).contiguous()
             gS_c = gS.contiguous()          # named: a temporary would be freed before the launch is enqueued
-            check(lib().b2_strain_sector_bwd(ptr(gS_c), ptr(u), ptr(tar_c), ptr(moments), ptr(table),
-                                             ptr(counts), ptr(du), B, T1, H, W, n_sectors, n_frames, stream()),
-                  "b2_strain_sector_bwd")
+            fs = ctx.frame.c_struct()
+            check(lib().b2_strain_sector_bwd_ex(ptr(gS_c), ptr(u), ptr(tar_c), ptr(moments), C.byref(fs),
+                                                ptr(counts), ptr(du), B, T1, H, W, n_sectors, n_frames, stream()),
+                  "b2_strain_sector_bwd_ex")
             _lib.count_launch()
             gu_tot = du
         g_reg = None
@@ -241,10 +283,13 @@ class ShootWarpStrainFunction(torch.autograd.Function):
 
 
 def _fused_size(H, W):
-    """Sizes served by a persistent fused kernel (they read strided cine volumes in place): one CTA per pair up to
-    128x128, one 4-CTA cluster per pair at 256x256 (unless B2_NO_CLUSTER selects the op-level path)."""
-    import os
-    return H == W and (H in (16, 32, 64, 128) or (H == 256 and not os.environ.get("B2_NO_CLUSTER")))
+    """Sizes served by a persistent fused forward kernel (they read strided cine volumes in place): one CTA per pair
+    up to 128x128, one 4-CTA cluster per pair at 256x256 - unless ``force_oplevel(fwd=True)`` is active."""
+    return H == W and H in (16, 32, 64, 128, 256) and not _flags["fwd"]
+
+
+def _fused_bwd_size(H, W):
+    return H == W and H in (16, 32, 64, 128, 256) and not _flags["bwd"]
 
 
 def _rows_dense(t):
@@ -252,7 +297,8 @@ def _rows_dense(t):
 
 
 def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T=1.0, n_sectors=N_SECTORS,
-                      n_frames=40, background="clamp", with_strain=True, loss_terms=False):
+                      n_frames=40, background="clamp", with_strain=True, loss_terms=False, theta0=None,
+                      clockwise=None):
     """Fused hot path for a batch of slices.
 
     v0: (B*T1, 2, H, W) initial velocities, slice-major; src_vol, tar_vol: (B,1,T1,H,W)
@@ -262,7 +308,8 @@ def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T
     Returns the dict ``forward_volume`` hands to the trainer plus 'displacement'.  With ``loss_terms=True`` the
     dict also holds 'registration_loss_terms' (P,2) = per pair {sum (tar - Sdef)^2, sum v.m}: the two reductions of
     RegistrationReconstructionLoss taken inside the shooting kernel (see :mod:`losses`); their backward needs no
-    seed tensors.
+    seed tensors.  ``theta0`` (radians) / ``clockwise``: per-slice sector frame of the strain matrix rows
+    (:mod:`strain`; DENSE_utils.py:196-204 of the reference) - scalars or B entries; default 0 / clockwise.
     """
     B, Cc, T1, H, W = tar_vol.shape
     if Cc != 1 or v0.shape != (B * T1, 2, H, W):
@@ -285,9 +332,9 @@ def shoot_warp_strain(v0, src_vol, tar_vol, metric: FluidMetric, num_steps=10, T
         src = src.contiguous() if shared else src_vol.reshape(B * T1, 1, H, W).contiguous()
         tar = tar_vol.reshape(B * T1, 1, H, W).contiguous()
     moments = mask_moments(mask0.contiguous()) if with_strain else None
-    table = sector_table(n_sectors, v0.device) if with_strain else None
+    frame = Frame(n_sectors, B, v0.device, theta0, clockwise) if with_strain else None
     m0, vel, u, sdef, S, lt = ShootWarpStrainFunction.apply(
-        v0, src, tar, moments, table, metric, int(num_steps), float(T), BG[background], int(n_sectors),
+        v0, src, tar, moments, frame, metric, int(num_steps), float(T), BG[background], int(n_sectors),
         int(n_frames), B, T1, not shared, bool(with_strain), int(src_ss), int(tar_ss), bool(loss_terms))
     out = {
         "strain_matrix": S,
@@ -313,6 +360,18 @@ def shoot_warp_pairs(v0, src, tar, metric: FluidMetric, num_steps=10, T=1.0, bac
     return out
 
 
+class PipelineResult:
+    """Handle of one :meth:`HostPipeline.submit`: ``get()`` blocks until the strain matrices of that call are
+    visible on the host and returns them (pinned tensor owned by the pipeline, valid until the call after next)."""
+
+    def __init__(self, S_host, done):
+        self._S, self.done = S_host, done
+
+    def get(self):
+        self.done.synchronize()
+        return self._S
+
+
 class HostPipeline:
     """Host-buffer entry point of the hot path: pinned host inputs in, strain matrices on the host out.
 
@@ -321,77 +380,97 @@ class HostPipeline:
     costs max(PCIe time, kernel time) instead of their sum.  Device outputs of the whole batch stay
     available in ``self.out`` (same keys as :func:`shoot_warp_strain`).  Inference only (no autograd).
 
-    The call is PCIe-bound, so binary masks cross the bus as one byte per pixel (``pack_masks=True``): a
-    multi-threaded host pass narrows each fp32 chunk to u8 while the previous copies are in flight and verifies that
-    every value is exactly 0 or 1 (the reference's cine inputs are binary myocardium masks); a chunk with any other
-    value is copied as fp32.  The device widens the bytes back into the fp32 staging volume - results are
-    bit-identical either way.  ``self.h2d_bytes`` is the number of bytes the last call copied to the device.
+    ``pipe(v0_host, vol_host)`` returns the (B,1,n_sectors,n_frames) strain matrices on the host AFTER the
+    device-to-host copy has completed (it waits on an event recorded behind the copy).  ``pipe.submit(...)`` is
+    the streaming form: it returns a :class:`PipelineResult` at once so that the next call's uploads overlap this
+    call's kernels; the inputs must stay untouched until ``result.get()`` returns, and two result buffers rotate,
+    so at most two calls may be outstanding.
+
+    Masks.  The reference's cine inputs are binary myocardium masks (README.md:21): ``vol_host`` may be ``uint8`` /
+    ``bool`` (one byte per pixel over PCIe, widened on the device by ``b2_unpack_u8`` - no host pass at all) or
+    ``float32``.  For fp32 volumes ``pack_masks=True`` narrows each chunk on the host (multi-threaded, verified to
+    be exactly 0/1, otherwise that chunk is copied as fp32) while the ``v0`` copy of the same chunk occupies the bus;
+    whether that pays is MEASURED: the pass is timed against the copy it has to hide behind and switched off for
+    later calls when it does not fit (few or busy host cores).  Results are bit-identical on every route.
+    ``self.h2d_bytes`` is the number of bytes the last call copied to the device.
     """
 
     def __init__(self, B, T, H, W, metric: FluidMetric, num_steps=10, T_end=1.0, n_sectors=N_SECTORS, n_frames=40,
-                 chunk_slices=None, device=None, background="clamp", pack_masks=True, pack_threads=0):
+                 chunk_slices=None, device=None, background="clamp", pack_masks=True, pack_threads=0, theta0=None,
+                 clockwise=None):
         self.dev = torch.device(device if device is not None else torch.cuda.current_device())
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.B, self.T, self.T1, self.H, self.W = B, T, T - 1, H, W
         self.metric, self.num_steps, self.T_end = metric, int(num_steps), float(T_end)
         self.n_sectors, self.n_frames, self.bg = int(n_sectors), int(n_frames), BG[background]
         if chunk_slices is None:      # four equal chunks: measured best at configs[1] (16 slices; 18 / 32 / 37 were slower)
             chunk_slices = -(-B // 4)
         self.chunk = max(1, min(int(chunk_slices), B))
-        self.copy_stream = torch.cuda.Stream(self.dev)
         dev, T1, cs = self.dev, self.T1, self.chunk
-        import os
-        self.pack_masks = bool(pack_masks) and (T * H * W) % 4 == 0 and os.environ.get("B2_PACK_MASKS") != "0"
+        self.byte_masks_ok = (T * H * W) % 4 == 0            # b2_unpack_u8 works on whole 4-byte words
+        self.pack_masks = bool(pack_masks) and self.byte_masks_ok
         if int(pack_threads) <= 0:    # CPUs this process may use, shared with the other ranks of the node
+            import os
             try:
                 ncpu = len(os.sched_getaffinity(0))
             except (AttributeError, OSError):
                 ncpu = os.cpu_count() or 1
             local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            share = ncpu // local_world
-            pack_threads = max(1, min(16, share))
-            # The narrowing pass must stay hidden behind the v0 copy of the same chunk and must not fight the other
-            # ranks for cores.  Measured on the 8-GPU box (32 host CPUs): 1 or 2 ranks (>= 12 threads each) gain 25 %
-            # (5.6 -> 4.25-4.4 ms per step); 4 ranks with 8 threads each lose (6.9 vs 5.9-6.4 ms) and 8 ranks with 4
-            # threads lose (15.3 vs 13.3 ms), so ranks with fewer than 12 host threads copy fp32.
-            if share < 12 and os.environ.get("B2_PACK_MASKS") != "1":      # B2_PACK_MASKS=1 forces the narrowing
-                self.pack_masks = False
+            pack_threads = max(1, min(16, ncpu // local_world))
         self.pack_threads = int(pack_threads)
         self._pack_s = self._pack_budget_s = 0.0
         self._pack_chunks = 0
-        self._pack_forced = os.environ.get("B2_PACK_MASKS") == "1"
         self.h2d_bytes = 0
-        # Three staging buffers: with two, the copy of chunk i+1 has to wait for the kernel of chunk i-1, which ends
-        # just about when the copy of chunk i does (kernel and copy times per chunk are nearly equal) - any jitter
-        # stalls the copy engine.
-        self.n_stages = 3
-        self._next_stage = 0
-        self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
-                       "v0": torch.empty((cs * T1, 2, H, W), device=dev),
-                       "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False}
-                      for _ in range(self.n_stages)]
-        if self.pack_masks:
-            for st in self.stage:
-                st["vol_u8"] = torch.empty(cs * T * H * W, dtype=torch.uint8, device=dev)
-                st["pack_host"] = torch.empty(cs * T * H * W, dtype=torch.uint8).pin_memory()
-        P = B * T1
-        self.out = _alloc_outputs(P, B, T1, H, W, dev, {"m0": True, "vel": True, "sdef": True, "S": True}, False,
-                                  self.n_sectors, self.n_frames, self.num_steps, False)
-        self.S_host = torch.empty((B, 1, self.n_sectors, self.n_frames), dtype=torch.float32).pin_memory()
-        self.table = sector_table(self.n_sectors, dev)
-        nbytes = lib().b2_shoot_workspace_bytes(cs, T1, H, W, self.num_steps)
-        self.ws = _workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            self.copy_stream = torch.cuda.Stream(dev)
+            # Three staging buffers: with two, the copy of chunk i+1 has to wait for the kernel of chunk i-1, which
+            # ends just about when the copy of chunk i does (kernel and copy times per chunk are nearly equal) - any
+            # jitter stalls the copy engine.
+            self.n_stages = 3
+            self._next_stage = 0
+            self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
+                           "v0": torch.empty((cs * T1, 2, H, W), device=dev),
+                           "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False}
+                          for _ in range(self.n_stages)]
+            if self.byte_masks_ok:
+                for st in self.stage:
+                    st["vol_u8"] = torch.empty(cs * T * H * W, dtype=torch.uint8, device=dev)
+                    st["pack_host"] = None        # pinned scratch of the fp32 narrowing pass, allocated on first use
+            P = B * T1
+            self.out = _alloc_outputs(P, B, T1, H, W, dev, {"m0": True, "vel": True, "sdef": True, "S": True}, False,
+                                      self.n_sectors, self.n_frames, self.num_steps, False)
+            self._S_host = [torch.empty((B, 1, self.n_sectors, self.n_frames), dtype=torch.float32).pin_memory()
+                            for _ in range(2)]
+            self._done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._next_result = 0
+            self.frame = Frame(self.n_sectors, B, dev, theta0, clockwise)
+            nbytes = lib().b2_shoot_workspace_bytes_flags(cs, T1, H, W, self.num_steps, _flags["fwd"])
+            self.ws = _workspace(nbytes, dev)
 
     def __call__(self, v0_host: torch.Tensor, vol_host: torch.Tensor):
-        """v0_host (B*(T-1),2,H,W), vol_host (B,1,T,H,W): pinned fp32 host tensors.  Returns S on the host."""
+        """v0_host (B*(T-1),2,H,W) pinned fp32, vol_host (B,1,T,H,W) pinned fp32 / uint8 / bool host tensors.
+        Returns S on the host, complete (the device-to-host copy has finished)."""
+        return self.submit(v0_host, vol_host).get()
+
+    def submit(self, v0_host: torch.Tensor, vol_host: torch.Tensor) -> PipelineResult:
         B, T, T1, H, W, cs = self.B, self.T, self.T1, self.H, self.W, self.chunk
         if tuple(vol_host.shape) != (B, 1, T, H, W) or tuple(v0_host.shape) != (B * T1, 2, H, W):
             raise _lib.B2Error(f"shape mismatch: v0 {tuple(v0_host.shape)}, vol {tuple(vol_host.shape)}")
+        if vol_host.dtype == torch.bool:
+            vol_host = vol_host.view(torch.uint8)
+        byte_masks = vol_host.dtype == torch.uint8
         if not (v0_host.is_contiguous() and vol_host.is_contiguous() and v0_host.dtype == torch.float32
-                and vol_host.dtype == torch.float32):
-            raise _lib.B2Error("HostPipeline expects contiguous fp32 host tensors")
-        main = torch.cuda.current_stream(self.dev)
+                and (byte_masks or vol_host.dtype == torch.float32)) or v0_host.is_cuda or vol_host.is_cuda:
+            raise _lib.B2Error("HostPipeline expects contiguous host tensors: fp32 v0, fp32 / uint8 / bool masks")
+        if byte_masks and not self.byte_masks_ok:
+            raise _lib.B2Error("uint8 masks need T*H*W to be a multiple of 4")
         self.h2d_bytes = 0
-        with torch.no_grad():
+        with torch.cuda.device(self.dev), torch.no_grad():
+            main = torch.cuda.current_stream(self.dev)
+            ri = self._next_result
+            self._next_result ^= 1
+            S_host, done = self._S_host[ri], self._done[ri]
             for i, b0 in enumerate(range(0, B, cs)):
                 b1 = min(b0 + cs, B)
                 nb = b1 - b0
@@ -403,26 +482,13 @@ class HostPipeline:
                     st["v0"][: nb * T1].copy_(v0_host[b0 * T1: b1 * T1], non_blocking=True)
                     self.h2d_bytes += nb * T1 * 2 * H * W * 4
                     n = nb * T * H * W
-                    packed = False
-                    if self.pack_masks:
-                        if st["used"]:
-                            st["ready"].synchronize()        # the copy out of this pinned pack buffer has finished
-                        # CPU pass (GIL released inside the call) while the v0 copy above occupies the bus
-                        t_pack = time.perf_counter()
-                        rc = lib().b2_pack_binary_u8_host(C.c_void_p(vol_host[b0:b1].data_ptr()),
-                                                          C.c_void_p(st["pack_host"].data_ptr()), n, self.pack_threads)
-                        if rc < 0:
-                            check(rc, "b2_pack_binary_u8_host")
-                        packed = rc == 1
-                        # safety net: the pass only pays while it hides behind the v0 copy of the same chunk
-                        # (~50 GB/s over PCIe); a starved host (few or busy cores) switches it off for later calls
-                        self._pack_s += time.perf_counter() - t_pack
-                        self._pack_budget_s += 0.8 * (nb * T1 * 2 * H * W * 4) / 50e9
-                        self._pack_chunks += 1
-                        if self._pack_chunks >= 16 and self._pack_s > self._pack_budget_s and not self._pack_forced:
-                            self.pack_masks = False
-                    if packed:
-                        st["vol_u8"][:n].copy_(st["pack_host"][:n], non_blocking=True)
+                    src_u8 = None
+                    if byte_masks:
+                        src_u8 = vol_host[b0:b1].reshape(-1)
+                    elif self.pack_masks:
+                        src_u8 = self._narrow_on_host(st, vol_host[b0:b1], n, nb * T1 * 2 * H * W * 4)
+                    if src_u8 is not None:
+                        st["vol_u8"][:n].copy_(src_u8[:n], non_blocking=True)
                         check(lib().b2_unpack_u8(ptr(st["vol_u8"]), ptr(st["vol"]), n,
                                                  C.c_void_p(self.copy_stream.cuda_stream)), "b2_unpack_u8")
                         _lib.count_launch()
@@ -437,14 +503,37 @@ class HostPipeline:
                 sl = slice(b0 * T1, b1 * T1)
                 out = {"u": self.out["u"][sl], "m0": self.out["m0"][sl], "vel": self.out["vel"][sl],
                        "sdef": self.out["sdef"][sl], "S": self.out["S"][b0:b1], "counts": self.out["counts"][b0:b1]}
-                _launch_shoot(st["v0"][: nb * T1], vol, vol.view(-1)[H * W:], mom, self.table, self.metric,
+                _launch_shoot(st["v0"][: nb * T1], vol, vol.view(-1)[H * W:], mom, self.frame, self.metric,
                               self.num_steps, self.T_end, self.bg, self.n_sectors, self.n_frames, nb, T1,
                               {}, False, False, False, out=out, ws=self.ws,
-                              src_slice_stride=T * H * W, tar_slice_stride=T * H * W)
+                              src_slice_stride=T * H * W, tar_slice_stride=T * H * W, first_slice=b0)
                 st["free"].record(main)
                 st["used"] = True
-                self.S_host[b0:b1].copy_(self.out["S"][b0:b1], non_blocking=True)
-        return self.S_host
+                S_host[b0:b1].copy_(self.out["S"][b0:b1], non_blocking=True)
+            done.record(main)                                            # behind the last device-to-host copy
+        return PipelineResult(S_host, done)
+
+    def _narrow_on_host(self, st, vol_chunk, n, v0_bytes):
+        """fp32 -> u8 on the host for one chunk; returns the pinned byte buffer, or None (copy as fp32)."""
+        import time
+        if st["pack_host"] is None:
+            st["pack_host"] = torch.empty(self.chunk * self.T * self.H * self.W, dtype=torch.uint8).pin_memory()
+        if st["used"]:
+            st["ready"].synchronize()        # the copy out of this pinned pack buffer has finished
+        # CPU pass (GIL released inside the call) while the v0 copy of this chunk occupies the bus
+        t_pack = time.perf_counter()
+        rc = lib().b2_pack_binary_u8_host(C.c_void_p(vol_chunk.data_ptr()), C.c_void_p(st["pack_host"].data_ptr()), n,
+                                          self.pack_threads)
+        if rc < 0:
+            check(rc, "b2_pack_binary_u8_host")
+        # measured decision: the pass only pays while it hides behind the v0 copy of the same chunk (~50 GB/s over
+        # PCIe); a starved host (few or busy cores, many ranks per node) switches it off for later calls
+        self._pack_s += time.perf_counter() - t_pack
+        self._pack_budget_s += 0.8 * v0_bytes / 50e9
+        self._pack_chunks += 1
+        if self._pack_chunks >= 8 and self._pack_s > self._pack_budget_s:
+            self.pack_masks = False
+        return st["pack_host"] if rc == 1 else None
 
     def result(self):
         """Device outputs of the last call, keyed like :func:`shoot_warp_strain`."""

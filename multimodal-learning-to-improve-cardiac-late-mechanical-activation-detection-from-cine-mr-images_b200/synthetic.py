@@ -15,22 +15,24 @@ import torch
 
 
 def synthetic_masks(B: int, T: int, H: int, W: int, seed: int = 2434, device="cpu") -> torch.Tensor:
-    """(B,1,T,H,W) fp32 binary annuli that contract and relax over the T frames."""
+    """(B,1,T,H,W) fp32 binary annuli that contract and relax over the T frames.  The per-slice random draws always
+    come from a CPU generator; the pixel arithmetic runs on ``device`` (large benchmark batches are built on the GPU;
+    tests build on the CPU and copy, so that oracle and CUDA path see the same bits)."""
     g = torch.Generator().manual_seed(seed)
-    dr = (torch.rand(B, generator=g) * 8 - 4).view(B, 1, 1, 1)
-    dc = (torch.rand(B, generator=g) * 8 - 4).view(B, 1, 1, 1)
-    phi0 = (torch.rand(B, generator=g) * 2 * math.pi).view(B, 1, 1, 1)
-    t = torch.arange(T, dtype=torch.float32).view(1, T, 1, 1)
+    dr = (torch.rand(B, generator=g) * 8 - 4).view(B, 1, 1, 1).to(device)
+    dc = (torch.rand(B, generator=g) * 8 - 4).view(B, 1, 1, 1).to(device)
+    phi0 = (torch.rand(B, generator=g) * 2 * math.pi).view(B, 1, 1, 1).to(device)
+    t = torch.arange(T, dtype=torch.float32, device=device).view(1, T, 1, 1)
     ph = torch.sin(math.pi * t / max(T - 1, 1))
     r_in = 0.18 * H * (1 - 0.25 * ph)
     r_out = 0.30 * H * (1 - 0.10 * ph)
-    rr = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1) - (H / 2 + dr)
-    cc = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W) - (W / 2 + dc)
+    rr = torch.arange(H, dtype=torch.float32, device=device).view(1, 1, H, 1) - (H / 2 + dr)
+    cc = torch.arange(W, dtype=torch.float32, device=device).view(1, 1, 1, W) - (W / 2 + dc)
     rad = torch.sqrt(rr * rr + cc * cc)
     theta = torch.atan2(rr, cc)
     mod = 1 + 0.05 * torch.cos(3 * theta + phi0)
     mask = ((rad >= r_in * mod) & (rad <= r_out * mod)).to(torch.float32)
-    return mask.unsqueeze(1).to(device)
+    return mask.unsqueeze(1)
 
 
 def synthetic_v0(P: int, H: int, W: int, seed: int = 7, max_disp: float = 3.0,

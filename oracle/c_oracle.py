@@ -41,7 +41,7 @@ def lib():
         L = C.CDLL(str(LIB))
         L.b2o_forward_volume.restype = C.c_int
         L.b2o_forward_volume.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_float] * 3 + [C.c_int] * 2 \
-            + [C.c_void_p] * 5 + [C.c_int]
+            + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2
         L.b2o_sector_table.restype = None
         L.b2o_sector_table.argtypes = [C.c_int, C.c_void_p]
         L.b2o_max_threads.restype = C.c_int
@@ -54,8 +54,10 @@ def max_threads() -> int:
 
 
 def forward_volume(v0: torch.Tensor, vol: torch.Tensor, params=(1.0, 0.1, 0.05), num_steps: int = 10,
-                   n_sectors: int = 126, n_frames: int = 40, nthreads: int = 0):
-    """v0 (B*(T-1),2,H,W), vol (B,1,T,H,W): fp32 CPU tensors.  Returns the forward_volume dict (Lagrangian split)."""
+                   n_sectors: int = 126, n_frames: int = 40, nthreads: int = 0, theta0=None, clockwise=None):
+    """v0 (B*(T-1),2,H,W), vol (B,1,T,H,W): fp32 CPU tensors.  Returns the forward_volume dict (Lagrangian split).
+    ``theta0`` (radians) / ``clockwise``: per-slice sector frame (B entries or scalars; default 0 / True).
+    ``nthreads`` > 0 sets the OpenMP team size explicitly (0 = OpenMP default, which OMP_NUM_THREADS caps)."""
     B, one, T, H, W = vol.shape
     assert one == 1 and tuple(v0.shape) == (B * (T - 1), 2, H, W)
     v0n = np.ascontiguousarray(v0.detach().cpu().numpy(), dtype=np.float32)
@@ -66,10 +68,16 @@ def forward_volume(v0: torch.Tensor, vol: torch.Tensor, params=(1.0, 0.1, 0.05),
     u = np.empty_like(m0)
     sdef = np.empty((P, 1, H, W), np.float32)
     S = np.empty((B, 1, n_sectors, n_frames), np.float32)
+    th = cw = None
+    if theta0 is not None:
+        th = np.ascontiguousarray(np.broadcast_to(np.asarray(theta0, np.float64).reshape(-1), (B,)))
+    if clockwise is not None:
+        cw = np.ascontiguousarray(np.broadcast_to(np.asarray(clockwise).reshape(-1) != 0, (B,)).astype(np.int32))
     rc = lib().b2o_forward_volume(v0n.ctypes.data, voln.ctypes.data, B, T, H, W, int(num_steps),
                                   float(params[0]), float(params[1]), float(params[2]), int(n_sectors), int(n_frames),
                                   m0.ctypes.data, vel.ctypes.data, u.ctypes.data, sdef.ctypes.data, S.ctypes.data,
-                                  int(nthreads))
+                                  int(nthreads), th.ctypes.data if th is not None else None,
+                                  cw.ctypes.data if cw is not None else None)
     if rc != 0:
         raise RuntimeError(f"b2o_forward_volume failed ({rc})")
     t = torch.from_numpy

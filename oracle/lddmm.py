@@ -234,9 +234,12 @@ class FluidMetric:
 # A.6  geodesic shooting
 # --------------------------------------------------------------------------- #
 def EPDiff_step(metric: FluidMetric, m0, dt: float, phiinv, conv: Conventions = DEFAULT,
-                return_mv: bool = False):
-    """One step of lagomorph.EPDiff_step."""
+                return_mv: bool = False, mommask=None):
+    """One step of lagomorph.EPDiff_step; the optional momentum mask multiplies the
+    transported momentum before ``sharp``."""
     m = Ad_star(phiinv, m0, conv)
+    if mommask is not None:
+        m = m * mommask
     v = metric.sharp(m)
     new = compose_disp_vel(phiinv, v, -dt, conv)
     if return_mv:
@@ -245,7 +248,7 @@ def EPDiff_step(metric: FluidMetric, m0, dt: float, phiinv, conv: Conventions = 
 
 
 def expmap(metric: FluidMetric, m0, T: float = 1.0, num_steps: int = 10, phiinv=None,
-           conv: Conventions = DEFAULT, trajectory: bool = False):
+           conv: Conventions = DEFAULT, trajectory: bool = False, mommask=None):
     """lagomorph.expmap: inverse-map displacement u with phi^-1(x) = x + u(x) (D4)."""
     u = torch.zeros_like(m0) if phiinv is None else phiinv
     dt = T / num_steps
@@ -253,10 +256,10 @@ def expmap(metric: FluidMetric, m0, T: float = 1.0, num_steps: int = 10, phiinv=
     for _ in range(num_steps):
         if trajectory:
             u_prev = u
-            u, m, v = EPDiff_step(metric, m0, dt, u_prev, conv, return_mv=True)
+            u, m, v = EPDiff_step(metric, m0, dt, u_prev, conv, return_mv=True, mommask=mommask)
             traj.append((u_prev, m, v))
         else:
-            u = EPDiff_step(metric, m0, dt, u, conv)
+            u = EPDiff_step(metric, m0, dt, u, conv, mommask=mommask)
     if trajectory:
         return u, traj
     return u

@@ -123,11 +123,13 @@ static inline float ddc(const float* f, int H, int W, int r, int c) {
   return 0.5f * (f[r * W + c + 1] - f[r * W + c - 1]);
 }
 
-/* D7: integer-only sector of direction (dr, dc); table[2k] = Q20 sin, table[2k+1] = Q20 cos */
-static int classify(long long dr, long long dc, const int32_t* tab, int n) {
+/* D7: integer-only sector of direction (dr, dc) in the slice's sector frame: table[2k] = Q20 sin, table[2k+1] =
+ * Q20 cos of theta0 + 2 pi k / n (start angle of the reference's mesh, DENSE_utils.py:198); clockwise == 0 numbers
+ * the sectors the other way round (DENSE_utils.py:201-204): k -> n-1-k */
+static int classify(long long dr, long long dc, const int32_t* tab, int n, double theta0, int clockwise) {
   if (dr == 0 && dc == 0) return -1;
-  double th = atan2((double)dr, (double)dc);
-  if (th < 0) th += 2.0 * M_PI;
+  double th = atan2((double)dr, (double)dc) - theta0;
+  th -= 2.0 * M_PI * floor(th / (2.0 * M_PI));
   int k = (int)floor(th / (2.0 * M_PI / n));
   if (k < 0) k = 0; if (k > n - 1) k = n - 1;
   for (int it = 0; it < n; ++it) {
@@ -138,28 +140,31 @@ static int classify(long long dr, long long dc, const int32_t* tab, int n) {
     else if (hi >= 0) k = k1;
     else break;
   }
-  return k;
+  return clockwise ? k : n - 1 - k;
 }
 
-void b2o_sector_table(int n, int32_t* tab) {
+void b2o_sector_table_rotated(int n, double theta0, int32_t* tab) {
   for (int k = 0; k < n; ++k) {
-    const double ang = 2.0 * M_PI * (double)k / (double)n;
+    const double ang = theta0 + 2.0 * M_PI * (double)k / (double)n;
     tab[2 * k] = (int32_t)llrint(1048576.0 * sin(ang));
     tab[2 * k + 1] = (int32_t)llrint(1048576.0 * cos(ang));
   }
 }
 
-/* Whole forward path for a batch of slices.  Outputs: m0, vel, u (P,2,H,W); sdef (P,1,H,W);
+void b2o_sector_table(int n, int32_t* tab) { b2o_sector_table_rotated(n, 0.0, tab); }
+
+/* Whole forward path for a batch of slices; theta0 (B doubles) / clockwise (B ints): per-slice sector frame, NULL = 0 / 1.  Outputs: m0, vel, u (P,2,H,W); sdef (P,1,H,W);
  * S (B,1,n_sectors,n_frames).  Returns 0, or -1 on bad sizes / allocation failure. */
 int b2o_forward_volume(const float* v0, const float* vol, int B, int T, int H, int W, int num_steps,
                        float alpha, float beta, float gamma, int n_sectors, int n_frames,
-                       float* m0_out, float* vel_out, float* u_out, float* sdef_out, float* S_out, int nthreads) {
+                       float* m0_out, float* vel_out, float* u_out, float* sdef_out, float* S_out, int nthreads,
+                       const double* theta0, const int* clockwise) {
   if (B < 1 || T < 2 || H < 2 || W < 2 || (H & (H - 1)) || (W & (W - 1)) || num_steps < 1 || n_sectors < 3) return -1;
   const int T1 = T - 1, N = H * W, P = B * T1;
   const float dt = 1.0f / (float)num_steps;
-  int32_t* tab = (int32_t*)malloc(sizeof(int32_t) * 2 * n_sectors);
+  int32_t* tab = (int32_t*)malloc(sizeof(int32_t) * 2 * n_sectors * (size_t)B);   /* one rotated table per slice */
   if (!tab) return -1;
-  b2o_sector_table(n_sectors, tab);
+  for (int b = 0; b < B; ++b) b2o_sector_table_rotated(n_sectors, theta0 ? theta0[b] : 0.0, tab + (size_t)b * 2 * n_sectors);
   memset(S_out, 0, sizeof(float) * (size_t)B * n_sectors * n_frames);
   int failed = 0;
 #ifdef _OPENMP
@@ -233,7 +238,8 @@ int b2o_forward_volume(const float* v0, const float* vol, int B, int T, int H, i
         for (int c = 0; c < W; ++c) {
           const int i = r * W + c;
           if (!(tar[i] > 0.5f)) continue;
-          const int k = classify(cnt * r - sx, cnt * c - sy, tab, n_sectors);
+          const int k = classify(cnt * r - sx, cnt * c - sy, tab + (size_t)b * 2 * n_sectors, n_sectors,
+                                 theta0 ? theta0[b] : 0.0, clockwise ? clockwise[b] : 1);
           if (k < 0) continue;
           const float G00 = 1.f + ddr(u, H, W, r, c), G01 = ddc(u, H, W, r, c);
           const float G10 = ddr(u + N, H, W, r, c), G11 = 1.f + ddc(u + N, H, W, r, c);

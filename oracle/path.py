@@ -62,7 +62,7 @@ def forward_pairs(v0, src, tar, metric: FluidMetric, num_steps: int = 10,
 
 def forward_volume(v0, src_vol, tar_vol, metric: FluidMetric, num_steps: int = 10,
                    n_sectors: int = N_SECTORS, n_frames: int | None = 40,
-                   conv: Conventions = DEFAULT):
+                   conv: Conventions = DEFAULT, theta0=None, clockwise=None):
     """``forward_volume`` contract of joint_registration_strainmat_LMA.py:307,314-318.
 
     v0: (B*(T-1), 2, H, W) ordered slice-major; src_vol, tar_vol: (B,1,T-1,H,W).
@@ -73,7 +73,7 @@ def forward_volume(v0, src_vol, tar_vol, metric: FluidMetric, num_steps: int = 1
     out = forward_pairs(v0, src, tar_vol.reshape(B * T1, 1, H, W), metric, num_steps, conv)
     u = out["displacement"]
     S = strain_matrix(u.reshape(B, T1, 2, H, W), tar_vol[:, 0], src_vol[:, 0, 0],
-                      n_sectors, n_frames, conv)
+                      n_sectors, n_frames, conv, theta0=theta0, clockwise=clockwise)
     return {
         "strain_matrix": S,
         "deformed_source": out["deformed_source"].reshape(B, 1, T1, H, W),

@@ -8,6 +8,12 @@ Nperseg=7 = 126 angular samples) together with the rotation equivariance of
 by -n*360/126 degrees rolls the strain rows by +n), which fixes the index
 direction: sector = floor(theta / (2*pi/126)) with theta = atan2(d_row, d_col).
 
+Sector frame of a slice: the reference's mesh starts at theta0 = arctan2(PositionB - PositionA)
+(DENSE_utils.py:198) and numbers its sectors clockwise (theta growing) or counter-clockwise per subject
+(``Clockwise`` flag, DENSE_utils.py:201-204).  ``theta0`` rotates the boundary table; ``clockwise=False`` maps
+index k -> n-1-k.  ``tests/golden/ref_sectors.npz`` (made by importing the reference's own ``spl2patchSA``) pins
+start angle, direction and count.
+
 Sector assignment is integer-only (D7) so CPU and GPU agree bit for bit:
 with cnt = sum(mask0), sx = sum(row*mask0), sy = sum(col*mask0) the direction of
 pixel (r, c) from the centroid is d = (cnt*r - sx, cnt*c - sy) (int64), and
@@ -29,10 +35,10 @@ DET_EPS = 1e-6
 RAD2_EPS = 1e-12
 
 
-def sector_boundaries(n_sectors: int = N_SECTORS) -> np.ndarray:
-    """(n, 2) int64 table of Q20 boundary directions (row, col)."""
+def sector_boundaries(n_sectors: int = N_SECTORS, theta0: float = 0.0) -> np.ndarray:
+    """(n, 2) int64 table of Q20 boundary directions (row, col), rotated by ``theta0`` radians."""
     k = np.arange(n_sectors, dtype=np.float64)
-    ang = 2.0 * math.pi * k / n_sectors
+    ang = float(theta0) + 2.0 * math.pi * k / n_sectors
     br = np.rint(Q * np.sin(ang)).astype(np.int64)
     bc = np.rint(Q * np.cos(ang)).astype(np.int64)
     return np.stack([br, bc], axis=1)
@@ -60,14 +66,15 @@ def centroid(cnt, sx, sy, H, W, dtype):
     return c0.to(dtype), c1.to(dtype)
 
 
-def classify_directions(dr: np.ndarray, dc: np.ndarray, n_sectors: int = N_SECTORS) -> np.ndarray:
-    """Integer-exact sector of int64 directions (dr, dc); -1 for the zero vector."""
-    tab = sector_boundaries(n_sectors)
+def classify_directions(dr: np.ndarray, dc: np.ndarray, n_sectors: int = N_SECTORS, theta0: float = 0.0,
+                        clockwise: bool = True) -> np.ndarray:
+    """Integer-exact sector of int64 directions (dr, dc) in the frame (theta0, clockwise); -1 for the zero vector."""
+    tab = sector_boundaries(n_sectors, theta0)
     br, bc = tab[:, 0], tab[:, 1]
     dr = np.asarray(dr, dtype=np.int64)
     dc = np.asarray(dc, dtype=np.int64)
-    theta = np.arctan2(dr.astype(np.float64), dc.astype(np.float64))
-    theta = np.where(theta < 0, theta + 2.0 * math.pi, theta)
+    theta = np.arctan2(dr.astype(np.float64), dc.astype(np.float64)) - float(theta0)
+    theta = np.mod(theta, 2.0 * math.pi)
     k = np.floor(theta / (2.0 * math.pi / n_sectors)).astype(np.int64) % n_sectors
     zero = (dr == 0) & (dc == 0)
     for _ in range(n_sectors):
@@ -81,19 +88,35 @@ def classify_directions(dr: np.ndarray, dc: np.ndarray, n_sectors: int = N_SECTO
         k = np.where(down, (k - 1) % n_sectors, np.where(up, k1, k))
     else:  # pragma: no cover - cannot happen for a valid boundary table
         raise RuntimeError("sector classification did not converge")
+    if not clockwise:
+        k = n_sectors - 1 - k
     return np.where(zero, -1, k).astype(np.int32)
 
 
-def sector_map(mask0: torch.Tensor, n_sectors: int = N_SECTORS) -> torch.Tensor:
-    """(B, H, W) int32 sector id of every pixel about the frame-0 mask centroid."""
+def _per_slice(x, B, default):
+    if x is None:
+        return [default] * B
+    a = np.asarray(x).reshape(-1)
+    if a.size == 1:
+        a = np.repeat(a, B)
+    assert a.size == B, f"{a.size} entries for {B} slices"
+    return list(a)
+
+
+def sector_map(mask0: torch.Tensor, n_sectors: int = N_SECTORS, theta0=None, clockwise=None) -> torch.Tensor:
+    """(B, H, W) int32 sector id of every pixel about the frame-0 mask centroid; ``theta0`` (radians) and
+    ``clockwise`` are scalars or one entry per slice (default 0 / True)."""
     B, H, W = mask0.shape
     cnt, sx, sy = mask_moments(mask0)
-    rr = np.arange(H, dtype=np.int64).reshape(1, H, 1)
-    cc = np.arange(W, dtype=np.int64).reshape(1, 1, W)
-    cntn = cnt.numpy().reshape(B, 1, 1)
-    dr = cntn * rr - sx.numpy().reshape(B, 1, 1) + 0 * cc
-    dc = cntn * cc - sy.numpy().reshape(B, 1, 1) + 0 * rr
-    return torch.from_numpy(classify_directions(dr, dc, n_sectors))
+    rr = np.arange(H, dtype=np.int64).reshape(H, 1)
+    cc = np.arange(W, dtype=np.int64).reshape(1, W)
+    th, cw = _per_slice(theta0, B, 0.0), _per_slice(clockwise, B, True)
+    out = np.empty((B, H, W), np.int32)
+    for b in range(B):
+        dr = int(cnt[b]) * rr - int(sx[b]) + 0 * cc
+        dc = int(cnt[b]) * cc - int(sy[b]) + 0 * rr
+        out[b] = classify_directions(dr, dc, n_sectors, float(th[b]), bool(cw[b]))
+    return torch.from_numpy(out)
 
 
 def strain_ecc(u: torch.Tensor, ctr0: torch.Tensor, ctr1: torch.Tensor, conv: Conventions = DEFAULT):
@@ -138,7 +161,7 @@ def align_frames(S: torch.Tensor, n_frames: int) -> torch.Tensor:
 
 def strain_matrix(u: torch.Tensor, tar: torch.Tensor, mask0: torch.Tensor,
                   n_sectors: int = N_SECTORS, n_frames: int | None = 40,
-                  conv: Conventions = DEFAULT, return_counts: bool = False):
+                  conv: Conventions = DEFAULT, return_counts: bool = False, theta0=None, clockwise=None):
     """Masked per-sector mean of Ecc.
 
     u: (B, T1, 2, H, W) inverse-map displacements of the T1 = T-1 frame-pairs of
@@ -149,7 +172,7 @@ def strain_matrix(u: torch.Tensor, tar: torch.Tensor, mask0: torch.Tensor,
     B, T1, _, H, W = u.shape
     cnt, sx, sy = mask_moments(mask0)
     c0, c1 = centroid(cnt, sx, sy, H, W, u.dtype)
-    sect = sector_map(mask0, n_sectors)                       # (B,H,W) int32
+    sect = sector_map(mask0, n_sectors, theta0, clockwise)    # (B,H,W) int32
     ecc, valid = strain_ecc(u.reshape(B * T1, 2, H, W),
                             c0.repeat_interleave(T1), c1.repeat_interleave(T1), conv)
     ecc = ecc.reshape(B, T1, H * W)

@@ -24,7 +24,12 @@ are for the callers either side of it:
 * ``merge_data_of_same_slice_from_batch``
                                        /root/reference/modules/trainer/joint_registration_regression_trainer.py:54-120
 
-Outputs ``tests/golden/ref_boundary.npz``, ``ref_augment.npz`` and ``ref_regroup.npz`` (committed).
+* ``spl2patchSA`` (the 126-sector polar mesh: start angle ``theta0 = arctan2(PositionB - PositionA)``, direction by
+  the ``Clockwise`` flag, 18 x 7 = 126 angular samples, mid-wall = layer 3) and ``SVDDenoise``
+                                       /root/reference/modules/data/utils/DENSE_utils.py:11-14,177-295
+  (PyQt5 is absent: stubbed, it is only used by an unrelated screen-size helper).
+
+Outputs ``tests/golden/ref_boundary.npz``, ``ref_augment.npz``, ``ref_regroup.npz`` and ``ref_sectors.npz`` (committed).
 """
 import importlib.util
 import json
@@ -39,6 +44,7 @@ REF = pathlib.Path("/root/reference")
 OUT = pathlib.Path(__file__).resolve().parent / "ref_boundary.npz"
 OUT_AUG = pathlib.Path(__file__).resolve().parent / "ref_augment.npz"
 OUT_REGROUP = pathlib.Path(__file__).resolve().parent / "ref_regroup.npz"
+OUT_SECTORS = pathlib.Path(__file__).resolve().parent / "ref_sectors.npz"
 SKROTATE_CALLS = []
 
 
@@ -125,6 +131,54 @@ def main():
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes, {len(out)} arrays)")
     make_augment_golden()
     make_regroup_golden()
+    make_sector_golden()
+
+
+def make_sector_golden():
+    """The reference's own sector mesh and SVD smoothing (DENSE_utils.py:177-295, :11-14) on synthetic contours.
+
+    ``spl2patchSA`` is run on two concentric circular contours (epicardium r = 110, endocardium r = 90) about
+    ``PositionA``; the centres of its 126 mid-wall faces (``layerid == 3``, DENSE_utils.py:323), in mesh order, are
+    the golden: face k must be classified as sector k by the oracle and by the CUDA classifier in the frame
+    (theta0, clockwise) of that case.  Contour points are (x, y) = (column, row) image coordinates."""
+    qt = types.ModuleType("PyQt5")
+    qt.QtWidgets = types.ModuleType("PyQt5.QtWidgets")
+    sys.modules.setdefault("PyQt5", qt)
+    sys.modules.setdefault("PyQt5.QtWidgets", qt.QtWidgets)
+    if not hasattr(np, "Inf"):
+        np.Inf = np.inf                      # DENSE_utils.py:152 uses the alias numpy 2 removed (singular solves only)
+    spec = importlib.util.spec_from_file_location("ref_dense_utils", REF / "modules/data/utils/DENSE_utils.py")
+    du = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(du)
+
+    ang = np.linspace(0.0, 2.0 * np.pi, 721)[:, None] + 0.00123          # closed polygons, vertices off the spokes
+    origin = np.array([128.0, 128.0])                                    # (x, y)
+    circle = lambda r: np.hstack([origin[0] + r * np.cos(ang), origin[1] + r * np.sin(ang)])  # noqa: E731
+    out = {"origin_xy": origin, "n_cases": np.int64(0)}
+    cases = [((200.0, 128.0), 1), ((200.0, 128.0), 0), ((160.0, 190.0), 1), ((160.0, 190.0), 0), ((100.0, 40.0), 1),
+             ((100.0, 40.0), 0)]
+    for i, (posB, cw) in enumerate(cases):
+        datamat = {
+            "ROIInfo": types.SimpleNamespace(RestingContour=[circle(110.0), circle(90.0)]),
+            "AnalysisInfo": types.SimpleNamespace(PositionA=origin.copy(), PositionB=np.array(posB), Clockwise=cw),
+        }
+        fv = du.spl2patchSA(datamat)
+        faces = fv["faces"][fv["layerid"] == 3] - 1                       # 0-based vertex ids of the mid-wall faces
+        assert faces.shape == (126, 4), faces.shape
+        centers = fv["vertices"][faces].mean(axis=1)                      # (126, 2) (x, y), mesh order
+        out[f"case{i}_posB_xy"] = np.array(posB)
+        out[f"case{i}_clockwise"] = np.int64(cw)
+        out[f"case{i}_theta0"] = np.float64(np.arctan2(posB[1] - origin[1], posB[0] - origin[0]))   # DENSE_utils.py:198
+        out[f"case{i}_midwall_centers_xy"] = centers
+        out[f"case{i}_sectorid"] = fv["sectorid"][fv["layerid"] == 3]
+    out["n_cases"] = np.int64(len(cases))
+    rng = np.random.default_rng(2434)
+    mat = rng.standard_normal((126, 40))
+    out["svd_in"] = mat
+    for rank in (3, 5):
+        out[f"svd_rank{rank}"] = du.SVDDenoise(mat.copy(), rank=rank)
+    np.savez_compressed(OUT_SECTORS, **out)
+    print(f"wrote {OUT_SECTORS} ({OUT_SECTORS.stat().st_size} bytes, {len(out)} arrays)")
 
 
 def make_regroup_golden():

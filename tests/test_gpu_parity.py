@@ -5,6 +5,8 @@ Tolerance (BASELINE.json north_star): 1e-5 relative for fp32 fields, measured as
 max|a-b| / max|b| (error relative to the field's scale); bit-exact for integer work
 (sector ids, mask moments, member counts).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -211,10 +213,11 @@ def test_expmap(pkg, oracle, dev, hw, S):
     assert torch.equal(pkg.expmap(mg, torch.zeros(1, 2, H, W, device=dev), num_steps=2), torch.zeros(1, 2, H, W, device=dev))
 
 
-def test_expmap_adjoint(pkg, oracle, dev):
-    """EPDiff adjoint (b2_shoot_bwd) vs autograd through the oracle."""
-    H = W = 32
-    S = 5
+@pytest.mark.parametrize("H,S", [(16, 5), (32, 5), (64, 4), (128, 3)])
+def test_expmap_adjoint(pkg, oracle, dev, H, S):
+    """EPDiff adjoint (b2_shoot_bwd) vs autograd through the oracle, every instantiation of the fused adjoint
+    kernel (<16,16,128>, <32,32,256>, <64,64,256>, <128,128,1024>)."""
+    W = H
     mg, mc = pkg.FluidMetric(PARAMS), oracle.FluidMetric(PARAMS)
     m0 = mc.flat(_smooth_v0(pkg, 2, H, W, 22, 2.0))
     _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S), lambda a: oracle.expmap(mc, a, num_steps=S), [m0],
@@ -478,18 +481,23 @@ def test_expmap_momentum_regulariser_gradient(pkg, oracle, dev):
                                      False, True)
     for oplevel in (False, True):
         gm = torch.empty_like(md)
-        nbytes = L.lib().b2_shoot_bwd_workspace_bytes(P, H, W)
+        a = L.ShootBwdArgs()
+        a.gu, a.g_reg, a.m0, a.traj, a.gv0 = gud.data_ptr(), grd.data_ptr(), md.data_ptr(), out["traj"].data_ptr(), gm.data_ptr()
+        a.P, a.H, a.W, a.num_steps, a.background, a.v0_is_momentum = P, H, W, S, 0, 1
+        a.flags = L.FLAG_OPLEVEL if oplevel else 0                    # explicit path flag (no environment variable)
+        a.alpha, a.beta, a.gamma, a.T = *PARAMS, 1.0
+        nbytes = L.lib().b2_shoot_bwd_workspace_bytes_flags(P, H, W, a.flags)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        import os
-        if oplevel:
-            os.environ["B2_BWD_OPLEVEL"] = "1"
-        try:
-            L.check(L.lib().b2_shoot_bwd_loss(L.ptr(gud), None, None, L.ptr(grd), L.ptr(md),
-                                              L.ptr(out["traj"]), L.ptr(gm), P, H, W, S, *PARAMS, 1.0, 0, 1, L.ptr(ws),
-                                              nbytes, L.stream()))
-        finally:
-            os.environ.pop("B2_BWD_OPLEVEL", None)
+        L.check(L.lib().b2_shoot_bwd_ex(C.byref(a), L.ptr(ws), nbytes, L.stream()))
         assert relerr(gm, mr.grad) < 5e-5, f"oplevel={oplevel}: {relerr(gm, mr.grad):.2e}"
+        # the legacy positional entry point is the same call with flags = 0
+        if not oplevel:
+            gm2 = torch.empty_like(md)
+            L.check(L.lib().b2_shoot_bwd_loss(L.ptr(gud), None, None, L.ptr(grd), L.ptr(md), L.ptr(out["traj"]),
+                                              L.ptr(gm2), P, H, W, S, *PARAMS, 1.0, 0, 1, L.ptr(ws), nbytes, L.stream()))
+            assert relerr(gm2, mr.grad) < 5e-5
+            assert L.lib().b2_shoot_bwd_loss(L.ptr(gud), None, None, L.ptr(grd), L.ptr(md), L.ptr(out["traj"]),
+                                             L.ptr(gm2), P, H, W, S, *PARAMS, 1.0, 0, 1, L.ptr(ws), 1024, L.stream()) == -6
 
 
 @pytest.mark.parametrize("shape", [(3, 4, 128, 128), (2, 3, 256, 256), (4, 2, 33, 47), (1, 1, 2, 2)])
@@ -793,3 +801,294 @@ def test_stream_ordered_and_graph_capturable(pkg, dev):
     for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
         assert torch.equal(cap[k], eager[k]), k
     assert torch.equal(cap_ops, eager_ops)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Round-2 parity at the BASELINE configurations (128x128 / 256x256, S = 10, more pairs than resident CTAs)
+# ------------------------------------------------------------------------------------------------------------------
+def _trainer_loss(out, tarv, sgt, crit=None):
+    """The configured training loss of the path's outputs (configs/config.json:169-181): reconstruction +
+    1000 x strain-matrix supervision."""
+    if crit is not None:
+        rec = crit(out, {"registration_target": tarv})
+    else:
+        rec = 0.5 * torch.mean((tarv - out["deformed_source"]) ** 2) / 0.03 ** 2 \
+            + 0.1 * (out["velocity"] * out["momentum"]).sum() / tarv.numel()
+    return rec + 1000.0 * torch.mean((out["strain_matrix"] - sgt) ** 2)
+
+
+@pytest.mark.parametrize("fused_terms", [False, True])
+def test_training_gradient_baseline_grid(pkg, oracle, dev, fused_terms):
+    """configs[2] kernel: gradient of the trainer loss (joint_registration_strainmat_LMA.py:190-194,307) through
+    shoot_warp_strain at 128x128, S = 10 - shoot_bwd_kernel<128,128,1024> - vs autograd through the torch oracle,
+    with and without the fused loss epilogue."""
+    B, T, H, W, S = 1, 4, 128, 128, 10
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 81, 3.0)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=82)
+    vc = v0.clone().requires_grad_(True)
+    lc = _trainer_loss(oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S), tar_vol, Sgt)
+    lc.backward()
+    vg = v0.to(dev).requires_grad_(True)
+    tv = tar_vol.to(dev)
+    out = pkg.shoot_warp_strain(vg, src_vol.to(dev), tv, pkg.FluidMetric(PARAMS), num_steps=S, loss_terms=fused_terms)
+    lg = _trainer_loss(out, tv, Sgt.to(dev), pkg.RegistrationReconstructionLoss(0.03, 0.1) if fused_terms else None)
+    lg.backward()
+    assert abs(lg.item() - lc.item()) < 1e-4 * abs(lc.item())
+    assert relerr(vg.grad, vc.grad) < 1e-4, f"{relerr(vg.grad, vc.grad):.2e}"
+    # and against the float64 oracle (ground truth of the adjoint)
+    vd = v0.double().requires_grad_(True)
+    _trainer_loss(oracle.forward_volume(vd, src_vol.double(), tar_vol.double(), oracle.FluidMetric(PARAMS), S),
+                  tar_vol.double(), Sgt.double()).backward()
+    own = relerr(vc.grad, vd.grad)
+    assert relerr(vg.grad, vd.grad) < max(1e-4, 3 * own), f"vs f64: {relerr(vg.grad, vd.grad):.2e} (oracle32: {own:.2e})"
+
+
+def test_training_gradient_256_fused_adjoint(pkg, oracle, dev):
+    """configs[3] grid: gradient of the trainer loss at 256x256 (S = 3 keeps the torch oracle's autograd in seconds)
+    through the fused cluster adjoint, vs the oracle and vs the op-level sweep."""
+    B, T, H, W, S = 1, 3, 256, 256, 3
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 83, 3.0)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=84)
+    vc = v0.clone().requires_grad_(True)
+    _trainer_loss(oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S), tar_vol, Sgt).backward()
+    grads = {}
+    for oplevel in (False, True):
+        vg = v0.to(dev).requires_grad_(True)
+        tv = tar_vol.to(dev)
+        with pkg.shooting.force_oplevel(bwd=oplevel):
+            out = pkg.shoot_warp_strain(vg, src_vol.to(dev), tv, pkg.FluidMetric(PARAMS), num_steps=S, loss_terms=True)
+            _trainer_loss(out, tv, Sgt.to(dev), pkg.RegistrationReconstructionLoss(0.03, 0.1)).backward()
+        grads[oplevel] = vg.grad
+        assert relerr(vg.grad, vc.grad) < 1e-4, f"oplevel={oplevel}: {relerr(vg.grad, vc.grad):.2e}"
+    assert relerr(grads[False], grads[True]) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", [(13, 25, 128, 128, 10), (3, 25, 256, 256, 10)])
+def test_multiwave_forward_vs_c_oracle(pkg, dev, cfg):
+    """More pairs than two waves of resident CTAs / clusters (312 > 2 x 148 at 128x128; 72 > 2 x 33 clusters at
+    256x256), S = 10 as in BASELINE.json: the persistent loop, the scratch ping-pong reuse, the bin re-zeroing and the
+    trailing barriers of the second and third pass over the grid, all five outputs of every pair vs the C oracle."""
+    from oracle import c_oracle
+    B, T, H, W, S = cfg
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 85, 3.0)
+    ref = c_oracle.forward_volume(v0, vol, PARAMS, S)
+    vd = vol.to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vd, "Lagrangian", 3)
+    out = pkg.shoot_warp_strain(v0.to(dev), sv, tv, pkg.FluidMetric(PARAMS), num_steps=S)
+    P = B * (T - 1)
+    for k in ("momentum", "velocity", "displacement"):
+        per_pair = (out[k].cpu() - ref[k]).abs().reshape(P, -1).max(dim=1)[0] / ref[k].abs().max()
+        assert per_pair.max() < TOL, f"{k}: worst pair {int(per_pair.argmax())} of {P}: {per_pair.max():.2e}"
+    sd = (out["deformed_source"].cpu() - ref["deformed_source"]).abs().reshape(P, -1).max(dim=1)[0]
+    assert sd.max() < 3e-5, f"deformed_source: worst pair {int(sd.argmax())}: {sd.max():.2e}"    # binary mask: |du| in px
+    assert relerr(out["strain_matrix"], ref["strain_matrix"]) < TOL
+    # last slice on its own (first wave of a fresh launch) reproduces the bits of its rows in the multi-wave run
+    sub = pkg.shoot_warp_strain(v0[-(T - 1):].to(dev), sv[-1:], tv[-1:], pkg.FluidMetric(PARAMS), num_steps=S)
+    assert torch.equal(sub["displacement"], out["displacement"][-(T - 1):])
+    assert torch.equal(sub["strain_matrix"], out["strain_matrix"][-1:])
+
+
+def test_multiwave_backward(pkg, oracle, dev):
+    """P = 160 > 148 resident CTAs at 128x128: the fused adjoint's second pass over the grid (scratch reuse) against
+    the op-level sweep on every pair, and against autograd through the oracle on the LAST pairs."""
+    B, T, H, W, S = 8, 21, 128, 128, 4
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    P = B * (T - 1)
+    v0 = _smooth_v0(pkg, P, H, W, 86, 3.0)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=87)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol.to(dev), "Lagrangian", 3)
+    crit = pkg.RegistrationReconstructionLoss(0.03, 0.1)
+    grads = {}
+    for oplevel in (False, True):
+        vg = v0.to(dev).requires_grad_(True)
+        with pkg.shooting.force_oplevel(bwd=oplevel):
+            out = pkg.shoot_warp_strain(vg, sv, tv, pkg.FluidMetric(PARAMS), num_steps=S, loss_terms=True)
+            _trainer_loss(out, tv, Sgt.to(dev), crit).backward()
+        grads[oplevel] = vg.grad.cpu()
+    per_pair = (grads[False] - grads[True]).abs().reshape(P, -1).max(dim=1)[0] / grads[True].abs().max()
+    assert per_pair.max() < 5e-5, f"worst pair {int(per_pair.argmax())}: {per_pair.max():.2e}"
+    # oracle spot check on the last slice (pairs 140..159, second wave): the loss is a sum over slices, so the
+    # gradient of the last slice's pairs is the gradient of that slice's own terms with the batch normalisation
+    src_vol, tar_vol = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    T1 = T - 1
+    vc = v0[-T1:].clone().requires_grad_(True)
+    oc = oracle.forward_volume(vc, src_vol[-1:], tar_vol[-1:], oracle.FluidMetric(PARAMS), S)
+    n_tar = tar_vol.numel()
+    lc = 0.5 * ((tar_vol[-1:] - oc["deformed_source"]) ** 2).sum() / n_tar / 0.03 ** 2 \
+        + 0.1 * (oc["velocity"] * oc["momentum"]).sum() / n_tar \
+        + 1000.0 * ((oc["strain_matrix"] - Sgt[-1:]) ** 2).sum() / Sgt.numel()
+    lc.backward()
+    assert relerr(grads[False][-T1:], vc.grad) < 1e-4, f"{relerr(grads[False][-T1:], vc.grad):.2e}"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Sector frame: per-slice theta0 + direction (DENSE_utils.py:196-204 of the reference)
+# ------------------------------------------------------------------------------------------------------------------
+def test_sector_frame_matches_reference_mesh_on_gpu(pkg, dev):
+    """Device classifier in the frame (theta0, clockwise) vs the reference's own spl2patchSA mesh: the pixel nearest
+    the centre of mid-wall face k is in sector k (tests/golden/ref_sectors.npz, made from the reference function)."""
+    import pathlib
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_sectors.npz")
+    ox, oy = g["origin_xy"]
+    H = W = 256
+    rr = torch.arange(H).view(H, 1).expand(H, W) - int(oy)
+    cc = torch.arange(W).view(1, W).expand(H, W) - int(ox)
+    rad2 = rr * rr + cc * cc
+    mask0 = ((rad2 >= 90 * 90) & (rad2 <= 110 * 110)).float()[None]        # symmetric: centroid == origin exactly
+    mom = pkg.strain.mask_moments(mask0.to(dev)).cpu()
+    assert mom[0, 1] == mom[0, 0] * int(oy) and mom[0, 2] == mom[0, 0] * int(ox)
+    n = int(g["n_cases"])
+    th = [float(g[f"case{i}_theta0"]) for i in range(n)]
+    cw = [bool(g[f"case{i}_clockwise"]) for i in range(n)]
+    sect = pkg.sector_map(mask0.expand(n, H, W).contiguous().to(dev), 126, theta0=th, clockwise=cw).cpu()
+    for i in range(n):
+        c = g[f"case{i}_midwall_centers_xy"]
+        px, py = np.rint(c[:, 0]).astype(int), np.rint(c[:, 1]).astype(int)
+        assert np.array_equal(sect[i, py, px].numpy(), np.arange(126)), i
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (128, 128), (256, 256), (64, 128)])
+def test_sector_frame_parity(pkg, oracle, dev, hw):
+    """Per-slice theta0 / direction through sector_map, strain_matrix (+ adjoint) and the fused kernels (single CTA,
+    cluster, op-level path): sector ids and member counts bit-exact vs the oracle, default frame unchanged."""
+    H, W = hw
+    B, T, S = 3, 3, 2
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    mask0, tar = src_vol[:, 0, 0].contiguous(), tar_vol[:, 0].contiguous()
+    th, cw = [0.83, -2.4, 0.0], [True, False, False]
+    assert torch.equal(pkg.sector_map(mask0.to(dev), 126, theta0=th, clockwise=cw).cpu(),
+                       oracle.sector_map(mask0, 126, th, cw))
+    assert torch.equal(pkg.sector_map(mask0.to(dev), 126, theta0=0.0, clockwise=True).cpu(), oracle.sector_map(mask0))
+    u = _smooth_v0(pkg, B * (T - 1), H, W, 91, 2.5).reshape(B, T - 1, 2, H, W)
+    Sc, cc = oracle.strain_matrix(u, tar, mask0, return_counts=True, theta0=th, clockwise=cw)
+    Sg, cg = pkg.strain_matrix(u.to(dev), tar.to(dev), mask0.to(dev), return_counts=True, theta0=th, clockwise=cw)
+    assert torch.equal(cg.cpu(), cc)
+    assert relerr(Sg, Sc) < TOL
+    _check_op(dev, lambda a: pkg.strain_matrix(a, tar.to(dev), mask0.to(dev), theta0=th, clockwise=cw),
+              lambda a: oracle.strain_matrix(a, tar, mask0, theta0=th, clockwise=cw), [u])
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 92, 3.0)
+    ref = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, theta0=th, clockwise=cw)
+    out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S,
+                                theta0=th, clockwise=cw)
+    assert relerr(out["strain_matrix"], ref["strain_matrix"]) < TOL
+    dflt = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S)
+    # slice 2 has theta0 = 0 and counter-clockwise numbering: its rows are the default rows reversed, bit for bit
+    assert torch.equal(out["strain_matrix"][2].flip(1), dflt["strain_matrix"][2])
+    assert not torch.equal(out["strain_matrix"][0], dflt["strain_matrix"][0])
+
+
+def test_sector_frame_rotation_equivariance(pkg, dev):
+    """A half turn of the cine batch with theta0 moved by pi gives the same strain-matrix rows; with theta0 left
+    alone the rows roll by 63 (affine.py:56-78); counter-clockwise numbering reverses the rows."""
+    B, T, H, W, S = 2, 3, 128, 128, 3
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W).to(dev)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 93, 2.0).to(dev)
+    m = pkg.FluidMetric(PARAMS)
+    rot = vol.flip(-1, -2)
+    v_rot = (-v0.flip(-1, -2)).contiguous()
+    th = [0.37, 2.1]
+    a = pkg.shoot_warp_strain(v0, *pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3), m, num_steps=S,
+                              theta0=th)["strain_matrix"]
+    b = pkg.shoot_warp_strain(v_rot, *pkg.data.split_vol_to_registration_pairs(rot, "Lagrangian", 3), m, num_steps=S,
+                              theta0=[t + np.pi for t in th])["strain_matrix"]
+    assert relerr(b, a) < 1e-3, f"{relerr(b, a):.2e}"
+    c = pkg.shoot_warp_strain(v0, *pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3), m, num_steps=S,
+                              theta0=th, clockwise=False)["strain_matrix"]
+    assert torch.equal(c.flip(2), a)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Host-side contracts fixed in round 2
+# ------------------------------------------------------------------------------------------------------------------
+def test_host_pipeline_returns_complete_result_and_takes_byte_masks(pkg, dev):
+    """``pipe(...)`` returns only after the device-to-host copy has completed (no caller-side synchronize), ``submit``
+    streams; uint8 / bool masks go over the bus as they are (1 B per pixel, no host pass) - same bits as fp32."""
+    B, T, H, W, S = 6, 5, 64, 64, 4
+    metric = pkg.FluidMetric(PARAMS)
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 95, 2.5).pin_memory()
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol.to(dev), "Lagrangian", 3)
+    th, cw = [0.1 * b for b in range(B)], [b % 2 == 0 for b in range(B)]
+    ref = pkg.shoot_warp_strain(v0.to(dev), sv, tv, metric, num_steps=S, theta0=th, clockwise=cw)["strain_matrix"].cpu()
+    torch.cuda.synchronize()
+    pipe = pkg.HostPipeline(B, T, H, W, metric, num_steps=S, chunk_slices=2, device=dev, theta0=th, clockwise=cw)
+    n_v0 = v0.numel() * 4
+    for host_vol, nbytes in ((vol.pin_memory(), None), (vol.to(torch.uint8).pin_memory(), vol.numel()),
+                             ((vol > 0.5).pin_memory(), vol.numel())):
+        got = pipe(v0, host_vol)                      # NO synchronize here: the call itself must have waited
+        assert torch.equal(got, ref), host_vol.dtype
+        if nbytes is not None:
+            assert pipe.h2d_bytes == n_v0 + nbytes
+    # streaming form: two calls in flight, results land in rotating host buffers
+    u8 = vol.to(torch.uint8).pin_memory()
+    r1 = pipe.submit(v0, u8)
+    r2 = pipe.submit(v0, u8)
+    assert torch.equal(r1.get(), ref) and torch.equal(r2.get(), ref)
+    with pytest.raises(RuntimeError):
+        pipe(v0, vol.to(torch.int32))
+
+
+def test_regroup_is_differentiable(pkg, oracle, dev):
+    """merge_data_of_same_slice_from_batch keeps the autograd graph (the joint trainer backpropagates the LMA loss
+    through it, joint_registration_regression_trainer.py:290-320): gradient == the reference construction's."""
+    rng = np.random.default_rng(7)
+    ids = [f"s{int(k)}" for k in rng.integers(0, 4, 23)]
+    P, H, W = len(ids), 32, 32
+    batch = {"slice_full_id": ids, "TOS": torch.rand(P, 126), "sector_LMA_labels": torch.randint(0, 2, (P, 126)),
+             "slice_LMA_label": torch.randint(0, 2, (P,))}
+    u = _rand(P, 2, H, W, seed=8)
+    for F in (3, 9):
+        uc = u.clone().requires_grad_(True)
+        want = oracle.path.merge_data_of_same_slice_from_batch(batch, {"displacement": uc}, F)["pred_displacement_fields"]
+        gout = _rand(*want.shape, seed=9)
+        want.backward(gout)
+        ug = u.to(dev).requires_grad_(True)
+        got = pkg.data.merge_data_of_same_slice_from_batch(batch, {"displacement": ug * 1.0}, F, dev)["pred_displacement_fields"]
+        assert got.grad_fn is not None
+        got.backward(gout.to(dev))
+        assert torch.equal(got.detach().cpu(), want.detach())
+        assert torch.equal(ug.grad.cpu(), uc.grad)          # a pure gather / scatter: bit exact
+
+
+def test_expmap_mommask_and_checkpoints(pkg, oracle, dev):
+    """``lagomorph.expmap(..., mommask=, checkpoints=)``: the momentum mask is applied in every step (step-by-step
+    path), ``checkpoints=True`` changes memory behaviour only - same geodesic, same gradient."""
+    H = W = 32
+    S = 4
+    mg, mc = pkg.FluidMetric(PARAMS), oracle.FluidMetric(PARAMS)
+    m0 = mc.flat(_smooth_v0(pkg, 2, H, W, 97, 2.0))
+    mask = (torch.rand(2, 1, H, W, generator=torch.Generator().manual_seed(98)) > 0.3).float()
+    _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S, mommask=mask.to(a.device)),
+              lambda a: oracle.expmap(mc, a, num_steps=S, mommask=mask), [m0], gtol=5e-5)
+    u_plain = pkg.expmap(mg, m0.to(dev), num_steps=S)
+    u_mask = pkg.expmap(mg, m0.to(dev), num_steps=S, mommask=mask.to(dev))
+    assert relerr(u_mask, u_plain) > 1e-3                              # the mask really takes part
+    _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S, checkpoints=True),
+              lambda a: oracle.expmap(mc, a, num_steps=S), [m0], gtol=5e-5)
+    assert torch.equal(pkg.expmap(mg, m0.to(dev), num_steps=S, checkpoints=True), u_plain)
+    # step-by-step path (explicit phiinv) with per-step checkpointing, as upstream does it
+    _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S, checkpoints=True, phiinv=torch.zeros_like(a)),
+              lambda a: oracle.expmap(mc, a, num_steps=S), [m0], gtol=5e-5)
+
+
+def test_ops_follow_the_tensors_device(pkg, dev):
+    """Launches go to the device (and that device's current stream) of the tensors, not to whatever device is
+    current: with a second GPU, ops on cuda:1 tensors while cuda:0 is current match the cuda:0 results."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d1 = torch.device("cuda:1")
+    I, u = _rand(2, 1, 32, 32, seed=1), 2.0 * _rand(2, 2, 32, 32, seed=2)
+    a = pkg.interp(I.to(dev), u.to(dev))
+    with torch.cuda.device(0):
+        b = pkg.interp(I.to(d1), u.to(d1))
+        vol = pkg.synthetic.synthetic_masks(2, 3, 32, 32)
+        v0 = _smooth_v0(pkg, 4, 32, 32, 3, 2.0)
+        o0 = pkg.shoot_warp_strain(v0.to(dev), *pkg.data.split_vol_to_registration_pairs(vol.to(dev), "Lagrangian", 3),
+                                   pkg.FluidMetric(PARAMS), num_steps=3)
+        o1 = pkg.shoot_warp_strain(v0.to(d1), *pkg.data.split_vol_to_registration_pairs(vol.to(d1), "Lagrangian", 3),
+                                   pkg.FluidMetric(PARAMS), num_steps=3)
+    assert b.device == d1 and torch.equal(a.cpu(), b.cpu())
+    assert all(torch.equal(o0[k].cpu(), o1[k].cpu()) for k in o0)

@@ -17,7 +17,7 @@ def test_header_symbols_exported(pkg):
     """The shared library loads and exports every entry point include/b2lddmm.h declares."""
     hdr = (ROOT / "include" / "b2lddmm.h").read_text()
     declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"b2_shoot_args"}
+    declared -= {"b2_shoot_args", "b2_shoot_bwd_args", "b2_sector_frame"}
     assert len(declared) >= 25
     L = ctypes.CDLL(str(pkg._lib.lib_path()))
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
@@ -33,6 +33,24 @@ def test_sector_table_matches_oracle(pkg, oracle):
         assert np.array_equal(np.array(list(buf)).reshape(n, 2), oracle.sector_boundaries(n))
     assert pkg._lib.lib().b2_sector_table_host(2, (ctypes.c_int32 * 4)()) == -5
     assert pkg._lib.lib().b2_sector_table_host(126, None) == -1
+    # rotated tables (per-slice sector frame): same integers as the oracle's for arbitrary start angles
+    for th in (0.0, 1.09432890732119, -1.878849107818673, 6.0, -0.3):
+        buf = (ctypes.c_int32 * (2 * 126))()
+        assert pkg._lib.lib().b2_sector_table_rotated_host(126, th, buf) == 0
+        assert np.array_equal(np.array(list(buf)).reshape(126, 2), oracle.sector_boundaries(126, th))
+    assert pkg._lib.lib().b2_sector_table_rotated_host(126, float("nan"), (ctypes.c_int32 * 252)()) == -5
+
+
+def test_struct_sizes_match_header(pkg):
+    L = pkg._lib.lib()
+    assert L.b2_sizeof_shoot_args() == ctypes.sizeof(pkg._lib.ShootArgs)
+    assert L.b2_sizeof_shoot_bwd_args() == ctypes.sizeof(pkg._lib.ShootBwdArgs)
+    # the adjoint workspace is sized per path: fused (resident CTAs x 3 fields) far below op-level (5 P fields)
+    fused = L.b2_shoot_bwd_workspace_bytes_flags(1536, 128, 128, 0)
+    oplevel = L.b2_shoot_bwd_workspace_bytes_flags(1536, 128, 128, pkg._lib.FLAG_OPLEVEL)
+    assert 0 < fused < oplevel / 10 and oplevel >= 5 * 1536 * 2 * 128 * 128 * 4
+    assert L.b2_shoot_bwd_workspace_bytes(1536, 128, 128) == fused
+    assert L.b2_shoot_bwd_workspace_bytes_flags(4, 100, 100, 0) > 0     # op-level sized; rejected at call time (FFT size)
 
 
 def test_argument_errors_without_gpu(pkg):
@@ -76,6 +94,31 @@ def test_models_interface(pkg):
     assert torch.linalg.matrix_rank(pkg.models.svd_smooth(S, 5)[0, 0]) == 5
 
 
+def test_svd_smooth_matches_reference_svddenoise(pkg):
+    """``svd_smooth`` vs the output of the reference's own ``SVDDenoise`` (DENSE_utils.py:11-14; golden made by
+    tests/golden/make_golden.py), both gradient modes; the projection gradient is U_r U_r^T g."""
+    g = np.load(ROOT / "tests" / "golden" / "ref_sectors.npz")
+    S = torch.from_numpy(g["svd_in"])                                    # float64, as the reference computes it
+    for rank in (3, 5):
+        want = torch.from_numpy(g[f"svd_rank{rank}"])
+        for mode in ("projection", "exact"):
+            got = pkg.models.svd_smooth(S[None, None], rank, grad=mode)[0, 0]
+            assert (got - want).abs().max() < 1e-12 * want.abs().max(), (rank, mode)
+        got32 = pkg.models.svd_smooth(S[None, None].float(), rank)[0, 0]
+        assert (got32.double() - want).abs().max() < 2e-5 * want.abs().max()      # fp32 SVD
+    x = S[None, None].clone().requires_grad_(True)
+    gout = torch.randn(1, 1, 126, 40, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    pkg.models.svd_smooth(x, 5).backward(gout)
+    U = torch.linalg.svd(S, full_matrices=False)[0][:, :5]
+    assert (x.grad[0, 0] - U @ (U.T @ gout[0, 0])).abs().max() < 1e-12
+    # rank-deficient input (edge-padded strain matrix): the projection gradient stays finite
+    pad = torch.cat([S[:, :20], S[:, 19:20].expand(126, 20)], dim=1)[None, None].clone().requires_grad_(True)
+    pkg.models.svd_smooth(pad, 5).sum().backward()
+    assert torch.isfinite(pad.grad).all()
+    with pytest.raises(ValueError):
+        pkg.models.svd_smooth(S[None, None], 5, grad="nope")
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
@@ -91,6 +134,15 @@ y = torch.randn(6, 126, generator=torch.Generator().manual_seed(2))
 loss = ((net(x[a:b])["TOS"] - y[a:b]) ** 2).sum() / 6 * ws   # so that the rank-average equals the full-batch grad
 loss.backward()
 n = pkg.parallel.allreduce_gradients(list(net.parameters()))
+# hook-driven reducer (all-reduce launched from inside backward, two buckets): same averaged gradient
+net2 = pkg.build_model({{"type": "NetStrainMat2LMA"}})
+net2.load_state_dict(net.state_dict())
+ps = list(net2.parameters())
+red = pkg.parallel.GradientAllReducer([ps[len(ps) // 2:], ps[:len(ps) // 2]])
+(((net2(x[a:b])["TOS"] - y[a:b]) ** 2).sum() / 6 * ws).backward()
+n2 = red.finish()
+err2 = max((p.grad - q.grad).abs().max().item() for p, q in zip(net.parameters(), net2.parameters()))
+assert n2 == 2 and err2 < 1e-6, (n2, err2)
 ref = pkg.build_model({{"type": "NetStrainMat2LMA"}})
 ref.load_state_dict(net.state_dict())
 (((ref(x)["TOS"] - y) ** 2).sum() / 6).backward()

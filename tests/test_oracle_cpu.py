@@ -379,3 +379,60 @@ def test_regroup_matches_reference(oracle, F):
     import pathlib
     g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_regroup.npz")
     check_regroup_against_golden(g, oracle.path.merge_data_of_same_slice_from_batch, F)
+
+
+def test_sector_frame_matches_reference_mesh(oracle):
+    """theta0 + direction of the sector classifier against the reference's own 126-sector mesh: the centres of the
+    mid-wall faces of ``spl2patchSA`` (DENSE_utils.py:177-295; golden made by importing the reference function) must
+    fall into sector k = their mesh index, for every start angle and both numbering directions."""
+    import pathlib
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "ref_sectors.npz")
+    o = g["origin_xy"]
+    assert int(g["n_cases"]) == 6
+    for i in range(int(g["n_cases"])):
+        c = g[f"case{i}_midwall_centers_xy"]                       # (126, 2) as (x, y) = (col, row)
+        theta0, cw = float(g[f"case{i}_theta0"]), bool(g[f"case{i}_clockwise"])
+        dr = np.rint(1000 * (c[:, 1] - o[1])).astype(np.int64)
+        dc = np.rint(1000 * (c[:, 0] - o[0])).astype(np.int64)
+        k = oracle.strain.classify_directions(dr, dc, 126, theta0, cw)
+        assert np.array_equal(k, np.arange(126)), (i, theta0, cw)
+        # 18 segments x 7 samples (DENSE_utils.py:178-188): AHA-style segment id of sector k is k // 7 + 1
+        assert np.array_equal(g[f"case{i}_sectorid"], np.arange(126) // 7 + 1)
+    # the default frame is the case theta0 = 0, clockwise: bit-identical to the frameless call
+    dr, dc = np.meshgrid(np.arange(-40, 41), np.arange(-40, 41), indexing="ij")
+    assert np.array_equal(oracle.strain.classify_directions(dr, dc, 126),
+                          oracle.strain.classify_directions(dr, dc, 126, 0.0, True))
+
+
+def test_sector_frame_equivariance(oracle):
+    """Shifting theta0 by j sector widths rolls the sector ids by -j; flipping the direction mirrors them."""
+    dr, dc = np.meshgrid(np.arange(-30, 31), np.arange(-30, 31), indexing="ij")
+    base = oracle.strain.classify_directions(dr, dc, 126, 0.4, True)
+    ok = base >= 0
+    w = 2 * np.pi / 126
+    for j in (1, 5, 125):
+        sh = oracle.strain.classify_directions(dr, dc, 126, 0.4 + j * w, True)
+        # boundaries are rounded to Q20 independently per table: pixels sitting exactly on a boundary may differ
+        frac = np.mean(((base - j) % 126)[ok] == sh[ok])
+        assert frac > 0.999, (j, frac)
+    ccw = oracle.strain.classify_directions(dr, dc, 126, 0.4, False)
+    assert np.array_equal(ccw[ok], 125 - base[ok])
+
+
+def test_c_oracle_sector_frame_matches_torch(oracle):
+    """Both oracles agree on the strain matrix in a rotated / flipped sector frame."""
+    from oracle import c_oracle
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    B, T, H, W, S = 3, 3, 32, 32, 2
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    v0 = pkg.synthetic.synthetic_v0(B * (T - 1), H, W, seed=5, max_disp=2.0)
+    th, cw = [0.7, -2.0, 0.0], [True, False, False]
+    src_vol, tar_vol = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    a = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric((1.0, 0.1, 0.05)), S, theta0=th, clockwise=cw)
+    b = c_oracle.forward_volume(v0, vol, (1.0, 0.1, 0.05), S, theta0=th, clockwise=cw)
+    d = oracle.forward_volume(v0, src_vol, tar_vol, oracle.FluidMetric((1.0, 0.1, 0.05)), S)
+    assert (a["strain_matrix"] - b["strain_matrix"]).abs().max() < 1e-5 * a["strain_matrix"].abs().max()
+    assert (a["strain_matrix"] - d["strain_matrix"]).abs().max() > 1e-3 * a["strain_matrix"].abs().max()
+    # slice 2 uses theta0 = 0 counter-clockwise: rows are the default rows reversed
+    assert torch.equal(a["strain_matrix"][2].flip(1), d["strain_matrix"][2])
