@@ -21,6 +21,7 @@
 //
 // Backward: shoot_bwd_kernel (fused EPDiff adjoint, square grids up to 128x128) or the op-level sweep.
 #include "fft.cuh"
+#include "shoot_params.cuh"
 #include "strain.cuh"
 
 namespace b2 {
@@ -36,14 +37,13 @@ int cluster_grid_clusters(int64_t P);
 int64_t cluster_workspace_bytes(int64_t P);
 int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t st);
 int64_t cluster_bwd_workspace_bytes(int64_t P);
-struct ShootBwdParams;
 int launch_shoot_cluster_bwd(const ShootBwdParams& prm, int background, cudaStream_t st);
 // 256x256 runs on the cluster kernels unless the caller asks for the op-level path or the device cannot
 // co-schedule a 4-CTA cluster with this much shared memory (then path B serves it)
 static bool cluster_size(int64_t H, int64_t W, int64_t P, int flags) {
   return H == 256 && W == 256 && !(flags & B2_FLAG_OPLEVEL) && cluster_grid_clusters(P) != 0;
 }
-constexpr bool kClusterBwd = false;   // fused 256x256 adjoint (shoot_cluster_bwd_kernel)
+constexpr bool kClusterBwd = true;    // fused 256x256 adjoint (shoot_cluster_bwd_kernel)
 static bool cluster_bwd_size(int64_t H, int64_t W, int64_t P, int flags) { return kClusterBwd && cluster_size(H, W, P, flags); }
 
 int epdiff_step_big(const float* u, const float* m0, float* unext, float* vout, void* zg, int64_t P, int64_t H,
@@ -350,9 +350,37 @@ static int launch_fused(const ShootParams& prm, int64_t grid, cudaStream_t st) {
 #define B2_BWD_U3A 8
 #endif
 #ifndef B2_BWD_U3B
-#define B2_BWD_U3B 2
+#define B2_BWD_U3B 4
 #endif
 constexpr int kBwdUnrollB1 = B2_BWD_U1, kBwdUnrollB3a = B2_BWD_U3A, kBwdUnrollB3b = B2_BWD_U3B;
+#ifndef B2_BWD_PREFETCH
+#define B2_BWD_PREFETCH 0
+#endif
+#ifndef B2_BWD_PIPE
+#define B2_BWD_PIPE 2     // software-pipeline depth (rows) of the compose adjoint's trajectory loads; 0 = off
+                          // (configs[2] training step: off 11.84 ms, 2: 11.61, 4: 11.66, 8: 11.62)
+#endif
+
+// L2 prefetch of one (u_s, v_s) trajectory entry (2 fields): the adjoint's first phase of a step touches them for
+// the first time (HBM latency on a dependent load chain); issued one phase earlier they arrive in L2 in time.
+// Variant 1: one prefetch.global.L2 per 128-byte line, spread over the CTA; variant 2: four bulk prefetches.
+template <int NT>
+__device__ __forceinline__ void prefetch_traj_l2(const float* us, const float* vs, int field_floats, int tid) {
+#if B2_BWD_PREFETCH == 1
+  for (int i = tid * 32; i < field_floats; i += NT * 32) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(us + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(vs + i));
+  }
+#elif B2_BWD_PREFETCH == 2
+  if (tid == 0) {
+    const unsigned bytes = (unsigned)(field_floats * sizeof(float));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(us), "r"(bytes));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vs), "r"(bytes));
+  }
+#else
+  (void)us; (void)vs; (void)field_floats; (void)tid;
+#endif
+}
 
 // ------------------------------------------------------------------ fused EPDiff adjoint (path A)
 // Reverse sweep over the saved trajectory, one CTA per frame-pair at a time, same residency scheme as the
@@ -360,19 +388,6 @@ constexpr int kBwdUnrollB1 = B2_BWD_U1, kBwdUnrollB3a = B2_BWD_U3A, kBwdUnrollB3
 // accumulators dL/du (ping-pong), dL/dm0 and w = m0 o (id + u_s) sit in per-CTA global scratch that stays in L2.
 // Buffers that receive float atomics (RED goes to L2) are only ever READ with ld.global.cg, so a stale L1 line
 // can never be observed; u_s, v_s and m0 are read-only for this kernel (ld.global.nc).
-struct ShootBwdParams {
-  const float* gu;      // dL/du^S   (P,2,H,W) or nullptr
-  const float* gvel;    // dL/dvel   or nullptr
-  const float* gm0;     // explicit dL/dm0 or nullptr
-  const float* g_reg;   // (P) dL/d(sum vel . m0) or nullptr: closed-form 2 g m0 (2 g vel) added to the result
-  const float* m0;
-  const float* traj;    // (S, 2, P, 2, H, W)
-  float* gv0;
-  float* scratch;       // per CTA: [G ping | G pong | dL/dm0]; w = m0 o (id + u_s) reuses the dead G buffer
-  int64_t P, field;
-  int num_steps, v0_is_momentum;
-  float alpha, beta, gamma, T;
-};
 
 template <int H, int W, int NT, int BG>
 __global__ void __launch_bounds__(NT)
@@ -428,6 +443,49 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
         }
         __syncthreads();
         SplatCarry cy{-1, 0.f, 0.f};
+#if B2_BWD_PIPE
+        // (u_s, v_s) are touched here for the first time: HBM latency on a dependent chain v_s -> taps -> u_s.
+        // Software pipeline over groups of kPipe rows: the v_s values of the NEXT group are loaded and the u_s
+        // lines around its pixels (the taps are within a pixel of them for |dt v| < 1) are pulled into L1 while
+        // the current group is processed.
+        constexpr int kPipe = B2_BWD_PIPE < NB ? B2_BWD_PIPE : NB;
+        static_assert(NB % kPipe == 0, "pipeline depth must divide the rows per thread");
+        float va[kPipe], vb[kPipe];
+#pragma unroll
+        for (int j = 0; j < kPipe; ++j) {
+          const int i = (rbase + j) * W + c;
+          va[j] = __ldg(vs + i);
+          vb[j] = __ldg(vs + N + i);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(us + i));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(us + N + i));
+        }
+        for (int k0 = 0; k0 < NB; k0 += kPipe) {
+          float na[kPipe], nb[kPipe];
+#pragma unroll
+          for (int j = 0; j < kPipe; ++j) {
+            const int kn = min(k0 + kPipe + j, NB - 1);          // last group: harmless re-read of its own rows
+            const int i = (rbase + kn) * W + c;
+            na[j] = __ldg(vs + i);
+            nb[j] = __ldg(vs + N + i);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(us + i));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(us + N + i));
+          }
+#pragma unroll
+          for (int j = 0; j < kPipe; ++j) {
+            const int r = rbase + k0 + j, i = r * W + c;
+            const float g0 = __ldcg(Gcur + i), g1 = __ldcg(Gcur + N + i);
+            const float v0 = va[j], v1 = vb[j];
+            const Taps t = make_taps<BG>((float)r + mdt * v0, (float)c + mdt * v1, H, W);
+            float a0, a1, b0, b1;
+            tap_grad<BG>(t, __ldg(us + t.o00), __ldg(us + t.o10), __ldg(us + t.o01), __ldg(us + t.o11), a0, a1);
+            tap_grad<BG>(t, __ldg(us + N + t.o00), __ldg(us + N + t.o10), __ldg(us + N + t.o01), __ldg(us + N + t.o11), b0, b1);
+            z[r * LD + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
+            splat2_agg<BG>(Gnext, N, t, g0, g1, cy, lane);
+          }
+#pragma unroll
+          for (int j = 0; j < kPipe; ++j) { va[j] = na[j]; vb[j] = nb[j]; }
+        }
+#else
 #pragma unroll (kBwdUnrollB1)
         for (int k = 0; k < NB; ++k) {
           const int r = rbase + k, i = r * W + c;
@@ -440,6 +498,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           z[r * LD + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
           splat2_agg<BG>(Gnext, N, t, g0, g1, cy, lane);
         }
+#endif
         splat_flush(Gnext, N, cy);
       } else {
         // u_0 = 0: u_1 = -dt v_0, so dL/dv_0 = -dt dL/du_1 (+ the direct gradient of the velocity output)
@@ -455,25 +514,23 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       // ---- dL/dm_s = sharp(dL/dv_s)   (self-adjoint)
       fluid_smem<H, W, true, NT>(z, twH, twW, csH, csW, fp, tid);
       if (s > 0) {
-        // ---- adjoint of m_s = (I + Du_s)^T (m0 o (id + u_s)); first w = m0 o (id + u_s) for the stencils.
-        // w goes into the buffer of dL/du_{s+1}, which is dead once the compose adjoint above has consumed it:
-        // three fields of scratch per CTA instead of four (57 MB instead of 76 MB over the resident CTAs).
-        float* Wb = Gcur;
+        // ---- adjoint of m_s = (I + Du_s)^T (m0 o (id + u_s)), w = m0 o (id + u_s), g = dL/dm_s:
+        //   dL/dm0 += splat_{x + u_s}((I + Du_s) g)                                  (REDs into A)
+        //   dL/du_s += (I + Du_s) g . grad m0(x + u_s)  +  D_0^T (g_0 w) + D_1^T (g_1 w)
+        // Pass A does everything that is local to a pixel with ONE gather of m0 (value and gradient from the same
+        // four taps) and leaves the four products g_a w_b behind: (g_1 w_0, g_1 w_1) in place of g in shared
+        // memory (column neighbours), (g_0 w_0, g_0 w_1) in the buffer of the consumed dL/du_{s+1} (row
+        // neighbours; three fields of scratch per CTA).  Pass B adds the transposed differences of the products.
+        float* Qb = Gcur;
+        if (s >= 2)      // the next adjoint step reads (u_{s-1}, v_{s-1}) first thing
+          prefetch_traj_l2<NT>(prm.traj + ((size_t)(2 * s - 2) * P + p) * prm.field,
+                               prm.traj + ((size_t)(2 * s - 1) * P + p) * prm.field, (int)prm.field, tid);
+        SplatCarry cy{-1, 0.f, 0.f};
 #pragma unroll (kBwdUnrollB3a)
         for (int k = 0; k < NB; ++k) {
           const int r = rbase + k, i = r * W + c;
-          const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
-          Wb[i] = tap_sample<BG>(t, __ldg(m0p + t.o00), __ldg(m0p + t.o10), __ldg(m0p + t.o01), __ldg(m0p + t.o11));
-          Wb[N + i] = tap_sample<BG>(t, __ldg(m0p + N + t.o00), __ldg(m0p + N + t.o10), __ldg(m0p + N + t.o01),
-                                     __ldg(m0p + N + t.o11));
-        }
-        __syncthreads();
-        SplatCarry cy{-1, 0.f, 0.f};
-#pragma unroll (kBwdUnrollB3b)
-        for (int k = 0; k < NB; ++k) {
-          const int r = rbase + k, i = r * W + c;
-          // the compose adjoint's REDs into Gnext completed before the barriers above: the own-pixel part of
-          // dL/du_s is a plain read-modify-write (L2 path on both sides), no atomic
+          // the compose adjoint's REDs into Gnext completed before the barriers above: the own-pixel parts of
+          // dL/du_s are plain read-modify-writes (L2 path on both sides), no atomic
           const float gn0 = __ldcg(Gnext + i), gn1 = __ldcg(Gnext + N + i);
           const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
           const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
@@ -485,25 +542,49 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           const float gw1 = g.y + (d10 * g.x + d11 * g.y);
           const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
           splat2_agg<BG>(A, N, t, gw0, gw1, cy, lane);
-          float a0, a1, b0, b1;
-          tap_grad<BG>(t, __ldg(m0p + t.o00), __ldg(m0p + t.o10), __ldg(m0p + t.o01), __ldg(m0p + t.o11), a0, a1);
-          tap_grad<BG>(t, __ldg(m0p + N + t.o00), __ldg(m0p + N + t.o10), __ldg(m0p + N + t.o01),
-                       __ldg(m0p + N + t.o11), b0, b1);
-          float o0 = gw0 * a0 + gw1 * b0;
-          float o1 = gw0 * a1 + gw1 * b1;
-          // Jacobian part: du_b += D_0^T (g_0 w_b) + D_1^T (g_1 w_b), gathered form
+          float w0, w1, o0, o1;
+          {
+            const float v00 = __ldg(m0p + t.o00), v10 = __ldg(m0p + t.o10), v01 = __ldg(m0p + t.o01), v11 = __ldg(m0p + t.o11);
+            float a0, a1;
+            w0 = tap_sample<BG>(t, v00, v10, v01, v11);
+            tap_grad<BG>(t, v00, v10, v01, v11, a0, a1);
+            o0 = gw0 * a0;
+            o1 = gw0 * a1;
+          }
+          {
+            const float v00 = __ldg(m0p + N + t.o00), v10 = __ldg(m0p + N + t.o10), v01 = __ldg(m0p + N + t.o01),
+                        v11 = __ldg(m0p + N + t.o11);
+            float b0, b1;
+            w1 = tap_sample<BG>(t, v00, v10, v01, v11);
+            tap_grad<BG>(t, v00, v10, v01, v11, b0, b1);
+            o0 += gw1 * b0;
+            o1 += gw1 * b1;
+          }
+          __stcg(Gnext + i, gn0 + o0);
+          __stcg(Gnext + N + i, gn1 + o1);
+          Qb[i] = g.x * w0;
+          Qb[N + i] = g.x * w1;
+          z[r * LD + c] = make_float2(g.y * w0, g.y * w1);     // own pixel only: nobody else reads g
+        }
+        splat_flush(A, N, cy);
+        __syncthreads();
+#pragma unroll (kBwdUnrollB3b)
+        for (int k = 0; k < NB; ++k) {
+          const int r = rbase + k, i = r * W + c;
+          const float gn0 = __ldcg(Gnext + i), gn1 = __ldcg(Gnext + N + i);
+          const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
+          const int oup = ru * W + c, odn = rd * W + c;
+          // gathered transposed differences (diffT): rows from the scratch products, columns from shared memory
           const float cmr = (r >= 1) ? diff_scale(r - 1, H) : 0.f, cpr = (r <= H - 2) ? diff_scale(r + 1, H) : 0.f;
           const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
-          const float gu_ = z[ru * LD + c].x, gd_ = z[rd * LD + c].x, gl_ = z[r * LD + cl].y, gr_ = z[r * LD + cr].y;
-          const float w0c = Wb[i], w1c = Wb[N + i];
-          o0 += (cmr * (gu_ * Wb[oup]) + c0r * (g.x * w0c) - cpr * (gd_ * Wb[odn]))
-              + (cmc * (gl_ * Wb[olf]) + c0c * (g.y * w0c) - cpc * (gr_ * Wb[ort]));
-          o1 += (cmr * (gu_ * Wb[N + oup]) + c0r * (g.x * w1c) - cpr * (gd_ * Wb[N + odn]))
-              + (cmc * (gl_ * Wb[N + olf]) + c0c * (g.y * w1c) - cpc * (gr_ * Wb[N + ort]));
+          const float2 ql = z[r * LD + cl], qr = z[r * LD + cr];
+          float o0 = (cmr * Qb[oup] - cpr * Qb[odn]) + (cmc * ql.x - cpc * qr.x);
+          float o1 = (cmr * Qb[N + oup] - cpr * Qb[N + odn]) + (cmc * ql.y - cpc * qr.y);
+          if (c0r != 0.f) { o0 += c0r * Qb[i]; o1 += c0r * Qb[N + i]; }                    // first / last image row
+          if (c0c != 0.f) { const float2 qc = z[r * LD + c]; o0 += c0c * qc.x; o1 += c0c * qc.y; }   // first / last column
           __stcg(Gnext + i, gn0 + o0);
           __stcg(Gnext + N + i, gn1 + o1);
         }
-        splat_flush(A, N, cy);
         float* tmp = Gcur; Gcur = Gnext; Gnext = tmp;
       } else {
         // m_0 = Ad*_0 m0 = m0 exactly: dL/dm0 = accumulated splats + dL/dm_0, summed in place in shared memory
@@ -519,6 +600,9 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       __syncthreads();
     }
     // ---- dL/dv0 = flat(dL/dm0)  (or dL/dm0 itself when the forward input was the momentum)
+    if (S >= 2 && p + gridDim.x < P)      // first trajectory entry the next pair of this CTA will read
+      prefetch_traj_l2<NT>(prm.traj + ((size_t)(2 * S - 2) * P + p + gridDim.x) * prm.field,
+                           prm.traj + ((size_t)(2 * S - 1) * P + p + gridDim.x) * prm.field, (int)prm.field, tid);
     if (!prm.v0_is_momentum) fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
     float* out = prm.gv0 + (size_t)p * prm.field;
     // d<sharp(m0), m0>/dm0 = 2 vel and flat(2 vel) = 2 m0: the regularisation gradient needs no transform

@@ -11,6 +11,7 @@
 #include <cooperative_groups.h>
 
 #include "fft.cuh"
+#include "shoot_params.cuh"
 #include "strain.cuh"
 
 namespace cg = cooperative_groups;
@@ -23,8 +24,6 @@ constexpr int kLDC = kSR + 1;      // column-slab pitch (256 rows x 65)
 constexpr int kCN = kCH * kCW;
 
 __constant__ int c_group_block[4][4] = {{0, 8, 1, 15}, {2, 14, 3, 13}, {4, 12, 5, 11}, {6, 10, 7, 9}};
-
-struct ShootBwdParams;
 
 struct ClusterParams {
   b2_shoot_args a;
@@ -385,8 +384,251 @@ int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t s
   return B2_OK;
 }
 
-// fused 256x256 adjoint: not built yet (shoot.cu: kClusterBwd)
-int64_t cluster_bwd_workspace_bytes(int64_t) { return 0; }
-int launch_shoot_cluster_bwd(const ShootBwdParams&, int, cudaStream_t) { return B2_E_FFTSIZE; }
+// ------------------------------------------------------------------ fused EPDiff adjoint at 256x256
+// Same reverse sweep as shoot_bwd_kernel (shoot.cu), one 4-CTA cluster per frame-pair, 64-row slabs.  dL/dv_s -> dL/dm_s
+// lives in the slab in shared memory (cluster_fluid is the self-adjoint sharp); the accumulators dL/du (ping-pong),
+// dL/dm0 and w = m0 o (id + u_s) sit in a per-cluster scratch that stays in L2 (4 fields = 2 MiB per cluster).  Every
+// scratch access is on the L2 path (ld.global.cg / st.global.cg / RED), so no stale L1 line can be observed across SMs.
+// Splats cross slab boundaries (float REDs into the shared scratch, pre-aggregated by splat2_agg); the only other
+// cross-slab data are the row-neighbour products g_0 w_b of the Ad* adjoint (L2).  The spectrum exchange of the fluid
+// operator reuses the consumed dL/du_{s+1} buffer (each CTA writes only its own slab rows of it, see zs_row).
+// Four cluster barriers per adjoint step.
+template <int BG>
+__global__ void __launch_bounds__(kCNT)
+shoot_cluster_bwd_kernel(const ShootBwdParams prm, const int64_t cluster_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rk = (int)cluster.block_rank();
+  const int64_t ncl = gridDim.x / kCL;
+  constexpr int H = kCH, W = kCW, N = kCN;
+  float2* z = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = z + (size_t)H * kLDC;
+  float2* cs = tw + 256;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int S = prm.num_steps;
+  const float mdt = -prm.T / (float)S;
+  const FluidParams fp{prm.alpha, prm.beta, prm.gamma, 1.0f / (float)N};
+  init_twiddles<256>(tw, tid, kCNT);
+  init_symbol_lut<256>(cs, tid, kCNT);
+  const int c = tid % W, br = tid / W;                 // cluster_fluid's slab <-> scratch map (rows strided by 4)
+  constexpr int NBc = kSR / (kCNT / W);                // 16 pixels per thread
+  const int r0 = rk * kSR;
+  const int lc = tid % kSR, q = lc / 16, cc = lc % 16;
+  const int pc = c_group_block[rk][q] * 16 + cc;
+  // pixel phases: a thread keeps one column and walks 16 CONSECUTIVE rows of the slab (splat2_agg carries the
+  // bottom-row contributions from row to row)
+  const int lrbase = br * NBc;
+  const int cl = max(c - 1, 0), cr = min(c + 1, W - 1);
+  const float sc = diff_scale(c, W);
+  const float cmc = (c >= 1) ? diff_scale(c - 1, W) : 0.f, cpc = (c <= W - 2) ? diff_scale(c + 1, W) : 0.f;
+  const float c0c = (c == W - 1 ? 1.f : 0.f) - (c == 0 ? 1.f : 0.f);
+  float* base = prm.scratch + (size_t)(blockIdx.x / kCL) * cluster_stride;
+  float* Ga = base;
+  float* Gb = Ga + 2 * (size_t)N;
+  float* A = Gb + 2 * (size_t)N;
+  float* Qb = A + 2 * (size_t)N;                       // (g_0 w_0, g_0 w_1): row-neighbour products of the Ad* adjoint
+  __syncthreads();
+
+  for (int64_t p = blockIdx.x / kCL; p < prm.P; p += ncl) {
+    const float* m0p = prm.m0 + (size_t)p * 2 * N;
+    float* Gcur = Ga;
+    float* Gnext = Gb;
+    for (int k = 0; k < NBc; ++k) {
+      const int i = (r0 + lrbase + k) * W + c;
+      __stcg(Gcur + i, prm.gu ? __ldg(prm.gu + (size_t)p * 2 * N + i) : 0.f);
+      __stcg(Gcur + N + i, prm.gu ? __ldg(prm.gu + (size_t)p * 2 * N + N + i) : 0.f);
+      __stcg(A + i, prm.gm0 ? __ldg(prm.gm0 + (size_t)p * 2 * N + i) : 0.f);
+      __stcg(A + N + i, prm.gm0 ? __ldg(prm.gm0 + (size_t)p * 2 * N + N + i) : 0.f);
+      __stcg(Gnext + i, 0.f);
+      __stcg(Gnext + N + i, 0.f);
+    }
+    cluster.sync();
+
+    for (int s = S - 1; s >= 0; --s) {
+      const float* us = prm.traj + ((size_t)(2 * s) * prm.P + p) * 2 * N;
+      const float* vs = prm.traj + ((size_t)(2 * s + 1) * prm.P + p) * 2 * N;
+      if (s > 0) {
+        // ---- adjoint of u_{s+1} = interp(u_s, v_s, -dt) - dt v_s : dL/dv_s -> z, splat of dL/du_{s+1} -> Gnext
+        SplatCarry cy{-1, 0.f, 0.f};
+#pragma unroll 2
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = lrbase + k, r = r0 + lr, i = r * W + c;
+          const float g0 = __ldcg(Gcur + i), g1 = __ldcg(Gcur + N + i);
+          const float v0 = __ldg(vs + i), v1 = __ldg(vs + N + i);
+          const Taps t = make_taps<BG>((float)r + mdt * v0, (float)c + mdt * v1, H, W);
+          float a0, a1, b0, b1;
+          tap_grad<BG>(t, __ldg(us + t.o00), __ldg(us + t.o10), __ldg(us + t.o01), __ldg(us + t.o11), a0, a1);
+          tap_grad<BG>(t, __ldg(us + N + t.o00), __ldg(us + N + t.o10), __ldg(us + N + t.o01), __ldg(us + N + t.o11), b0, b1);
+          z[lr * kLDR + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
+          splat2_agg<BG>(Gnext, N, t, g0, g1, cy, lane);
+        }
+        splat_flush(Gnext, N, cy);
+      } else {
+        // u_0 = 0: u_1 = -dt v_0, so dL/dv_0 = -dt dL/du_1 (+ the direct gradient of the velocity output)
+        const float* gv = prm.gvel ? prm.gvel + (size_t)p * 2 * N : nullptr;
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = lrbase + k, i = (r0 + lr) * W + c;
+          float a = mdt * __ldcg(Gcur + i), b = mdt * __ldcg(Gcur + N + i);
+          if (gv) { a += __ldg(gv + i); b += __ldg(gv + N + i); }
+          z[lr * kLDR + c] = make_float2(a, b);
+        }
+      }
+      __syncthreads();
+      // ---- dL/dm_s = sharp(dL/dv_s); the spectrum is exchanged through the consumed dL/du_{s+1} buffer
+      cluster_fluid<true>(cluster, z, tw, cs, reinterpret_cast<float2*>(Gcur), fp, tid, rk, r0, c, br, lc, q, pc);
+      if (s > 0) {
+        // ---- adjoint of m_s = (I + Du_s)^T (m0 o (id + u_s)) in two passes, as in shoot_bwd_kernel: pass A does
+        // everything local to a pixel with one gather of m0 and leaves the products g_a w_b behind - (g_1 w_0,
+        // g_1 w_1) in place of g in the slab (column neighbours never leave the slab), (g_0 w_0, g_0 w_1) in the
+        // scratch field Qb (row neighbours cross slab boundaries: L2) - pass B adds their transposed differences.
+        SplatCarry cy{-1, 0.f, 0.f};
+#pragma unroll 2
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = lrbase + k, r = r0 + lr, i = r * W + c;
+          const float gn0 = __ldcg(Gnext + i), gn1 = __ldcg(Gnext + N + i);
+          const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
+          const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
+          const float sr = diff_scale(r, H);
+          const float d00 = sr * (__ldg(us + odn) - __ldg(us + oup)), d10 = sr * (__ldg(us + N + odn) - __ldg(us + N + oup));
+          const float d01 = sc * (__ldg(us + ort) - __ldg(us + olf)), d11 = sc * (__ldg(us + N + ort) - __ldg(us + N + olf));
+          const float2 g = z[lr * kLDR + c];
+          const float gw0 = g.x + (d00 * g.x + d01 * g.y);
+          const float gw1 = g.y + (d10 * g.x + d11 * g.y);
+          const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
+          splat2_agg<BG>(A, N, t, gw0, gw1, cy, lane);
+          float w0, w1, o0, o1;
+          {
+            const float v00 = __ldg(m0p + t.o00), v10 = __ldg(m0p + t.o10), v01 = __ldg(m0p + t.o01), v11 = __ldg(m0p + t.o11);
+            float a0, a1;
+            w0 = tap_sample<BG>(t, v00, v10, v01, v11);
+            tap_grad<BG>(t, v00, v10, v01, v11, a0, a1);
+            o0 = gw0 * a0;
+            o1 = gw0 * a1;
+          }
+          {
+            const float v00 = __ldg(m0p + N + t.o00), v10 = __ldg(m0p + N + t.o10), v01 = __ldg(m0p + N + t.o01),
+                        v11 = __ldg(m0p + N + t.o11);
+            float b0, b1;
+            w1 = tap_sample<BG>(t, v00, v10, v01, v11);
+            tap_grad<BG>(t, v00, v10, v01, v11, b0, b1);
+            o0 += gw1 * b0;
+            o1 += gw1 * b1;
+          }
+          __stcg(Gnext + i, gn0 + o0);          // own pixel: the compose adjoint's REDs completed two barriers ago
+          __stcg(Gnext + N + i, gn1 + o1);
+          __stcg(Qb + i, g.x * w0);
+          __stcg(Qb + N + i, g.x * w1);
+          z[lr * kLDR + c] = make_float2(g.y * w0, g.y * w1);
+        }
+        splat_flush(A, N, cy);
+        cluster.sync();                          // row-neighbour products of the adjacent slabs are visible
+#pragma unroll 2
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = lrbase + k, r = r0 + lr, i = r * W + c;
+          const float gn0 = __ldcg(Gnext + i), gn1 = __ldcg(Gnext + N + i);
+          const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
+          const int oup = ru * W + c, odn = rd * W + c;
+          const float cmr = (r >= 1) ? diff_scale(r - 1, H) : 0.f, cpr = (r <= H - 2) ? diff_scale(r + 1, H) : 0.f;
+          const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
+          const float2 ql = z[lr * kLDR + cl], qr = z[lr * kLDR + cr];
+          float o0 = (cmr * __ldcg(Qb + oup) - cpr * __ldcg(Qb + odn)) + (cmc * ql.x - cpc * qr.x);
+          float o1 = (cmr * __ldcg(Qb + N + oup) - cpr * __ldcg(Qb + N + odn)) + (cmc * ql.y - cpc * qr.y);
+          if (c0r != 0.f) { o0 += c0r * __ldcg(Qb + i); o1 += c0r * __ldcg(Qb + N + i); }
+          if (c0c != 0.f) { const float2 qc = z[lr * kLDR + c]; o0 += c0c * qc.x; o1 += c0c * qc.y; }
+          __stcg(Gnext + i, gn0 + o0);
+          __stcg(Gnext + N + i, gn1 + o1);
+          __stcg(Gcur + i, 0.f);                // becomes the splat target of the next step (dead since the exchange)
+          __stcg(Gcur + N + i, 0.f);
+        }
+        float* tmp = Gcur; Gcur = Gnext; Gnext = tmp;
+        cluster.sync();   // dL/dm0 REDs, product reads and the zero fill are complete cluster-wide
+      } else {
+        // m_0 = Ad*_0 m0 = m0 exactly: dL/dm0 = accumulated splats + dL/dm_0, summed in place in the slab
+        for (int k = 0; k < NBc; ++k) {
+          const int lr = lrbase + k, i = (r0 + lr) * W + c;
+          float2 g = z[lr * kLDR + c];
+          g.x += __ldcg(A + i);
+          g.y += __ldcg(A + N + i);
+          z[lr * kLDR + c] = g;
+        }
+        __syncthreads();
+      }
+    }
+    // ---- dL/dv0 = flat(dL/dm0)  (or dL/dm0 itself when the forward input was the momentum)
+    if (!prm.v0_is_momentum)
+      cluster_fluid<false>(cluster, z, tw, cs, reinterpret_cast<float2*>(Gcur), fp, tid, rk, r0, c, br, lc, q, pc);
+    float* out = prm.gv0 + (size_t)p * 2 * N;
+    const float g2 = prm.g_reg ? 2.f * __ldg(prm.g_reg + p) : 0.f;
+    const float* radd = prm.v0_is_momentum ? prm.traj + ((size_t)prm.P + p) * 2 * N : m0p;   // v_0 of the trajectory
+    for (int k = 0; k < NBc; ++k) {
+      const int lr = lrbase + k, i = (r0 + lr) * W + c;
+      float2 v = z[lr * kLDR + c];
+      if (prm.g_reg) { v.x += g2 * __ldg(radd + i); v.y += g2 * __ldg(radd + N + i); }
+      out[i] = v.x;
+      out[N + i] = v.y;
+    }
+    cluster.sync();   // scratch and slab free for the next pair of this cluster
+  }
+}
+
+static size_t cluster_bwd_scratch_floats() { return (size_t)8 * kCN; }   // 4 fields: G ping, G pong, dL/dm0, products
+
+template <int BG>
+static int cluster_bwd_max_active(int* out) {
+  B2_CUDA(cudaFuncSetAttribute(shoot_cluster_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCL * 64);
+  cfg.blockDim = dim3(kCNT);
+  cfg.dynamicSmemBytes = kClusterSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  B2_CUDA(cudaOccupancyMaxActiveClusters(&n, shoot_cluster_bwd_kernel<BG>, &cfg));
+  *out = n;
+  return B2_OK;
+}
+
+static int cluster_bwd_grid_clusters(int64_t P) {
+  static int cached = -1;
+  if (cached < 0) {
+    int n = 0;
+    if (cluster_bwd_max_active<B2_BG_CLAMP>(&n) != B2_OK || n < 1) { (void)cudaGetLastError(); return 0; }
+    cached = n;
+  }
+  return (int)(cached < P ? cached : P);
+}
+
+int64_t cluster_bwd_workspace_bytes(int64_t P) {
+  int n = cluster_bwd_grid_clusters(P);
+  if (n < 1) n = 37 < P ? 37 : (int)P;                 // size query without a device: assume a full B200
+  return (int64_t)(sizeof(float) * cluster_bwd_scratch_floats() * (size_t)n);
+}
+
+int launch_shoot_cluster_bwd(const ShootBwdParams& prm, int background, cudaStream_t st) {
+  const int ncl = cluster_bwd_grid_clusters(prm.P);
+  if (ncl < 1) return B2_E_FFTSIZE;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(kCL * ncl));
+  cfg.blockDim = dim3(kCNT);
+  cfg.dynamicSmemBytes = kClusterSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int64_t stride = (int64_t)cluster_bwd_scratch_floats();
+  if (background == B2_BG_CLAMP) {
+    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_bwd_kernel<B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_bwd_kernel<B2_BG_CLAMP>, prm, stride));
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(shoot_cluster_bwd_kernel<B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+    B2_CUDA(cudaLaunchKernelEx(&cfg, shoot_cluster_bwd_kernel<B2_BG_ZERO>, prm, stride));
+  }
+  return B2_OK;
+}
 
 }  // namespace b2

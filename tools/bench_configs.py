@@ -149,12 +149,13 @@ def c4_sharded(pkg, dev, dist=None, B=256, T=50, H=256, W=256, steps=2, warmup=1
     world = dist.get_world_size() if dist is not None else 1
     b0, b1 = pkg.parallel.shard_slices(B, rank, world)
     nb, T1 = b1 - b0, T - 1
-    vol = pkg.synthetic.synthetic_masks(B, T, H, W, seed=2434)[b0:b1].to(dev)       # this rank's slices of the batch
+    vol = pkg.synthetic.synthetic_masks(nb, T, H, W, seed=2434 + b0, device=dev)    # this rank's slices, built on the GPU
     v0 = device_v0(pkg, nb * T1, H, W, 1000 + b0, dev, chunk=784)
     src_vol, tar_vol = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
     keep = {}
 
     def step():
+        keep["out"] = None        # free the previous outputs first: the caching allocator reuses the blocks (no cudaMalloc)
         with torch.no_grad():
             keep["out"] = pkg.shoot_warp_strain(v0, src_vol, tar_vol, metric, num_steps=S_STEPS)
 
