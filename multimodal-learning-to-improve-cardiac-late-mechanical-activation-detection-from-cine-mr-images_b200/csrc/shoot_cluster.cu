@@ -18,12 +18,27 @@ namespace cg = cooperative_groups;
 
 namespace b2 {
 
-constexpr int kCH = 256, kCW = 256, kCL = 4, kCNT = 1024, kSR = kCH / kCL;   // slab rows per CTA
+// Cluster shape (compile-time): 4 CTAs x 1024 threads with 64-row slabs (one CTA per SM), or 8 CTAs x 512 threads with
+// 32-row slabs (two CTAs per SM: two barrier domains per SM, and 8-CTA clusters of half-size CTAs pack the GPCs'
+// SM counts better than 4 whole SMs do).  Work per thread is identical: 16 pixels, one radix-16 task per FFT pass.
+#ifndef B2_CLUSTER_CTAS
+#define B2_CLUSTER_CTAS 4
+#endif
+constexpr int kCH = 256, kCW = 256, kCL = B2_CLUSTER_CTAS, kCNT = 4096 / kCL, kSR = kCH / kCL;   // slab rows per CTA
+constexpr int kCtasPerSM = kCL / 4;                          // launch bound: 1 (1024 threads) or 2 (512 threads)
+static_assert(kCL == 4 || kCL == 8, "cluster of 4 or 8 CTAs");
 constexpr int kLDR = kCW + 1;      // row-slab pitch   (64 rows x 257)
 constexpr int kLDC = kSR + 1;      // column-slab pitch (256 rows x 65)
 constexpr int kCN = kCH * kCW;
 
+// mirror-closed groups of spectrum-cell blocks (16 cells each; the mirror of block b is block (16 - b) % 16)
+#if B2_CLUSTER_CTAS == 4
 __constant__ int c_group_block[4][4] = {{0, 8, 1, 15}, {2, 14, 3, 13}, {4, 12, 5, 11}, {6, 10, 7, 9}};
+__device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? (q < 2 ? q : 5 - q) : (q ^ 1); }
+#else
+__constant__ int c_group_block[8][2] = {{0, 8}, {1, 15}, {2, 14}, {3, 13}, {4, 12}, {5, 11}, {6, 10}, {7, 9}};
+__device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? q : (q ^ 1); }     // blocks 0 and 8 mirror onto themselves
+#endif
 
 struct ClusterParams {
   b2_shoot_args a;
@@ -32,16 +47,15 @@ struct ClusterParams {
   int64_t cluster_stride;   // floats of scratch per cluster
 };
 
-__device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? (q < 2 ? q : 5 - q) : (q ^ 1); }
-
 // The spectrum exchange buffer Zs (one complex field) has no memory of its own: it lives in the 2-plane field that
 // the coming compose will overwrite with u_{s+1} (dead until then).  Row r of the spectrum is placed so that the rows
 // CTA X reads LAST (its own slab, second exchange) occupy exactly the bytes X itself writes in that compose - rows
 // 64X .. 64X+31 in X's part of plane 0, rows 64X+32 .. 64X+63 in X's part of plane 1 - so no CTA can overwrite
 // spectrum rows another CTA still has to read, and the cluster needs no extra barrier.  Index in float2 units.
 __device__ __forceinline__ int zs_row(int r) {
-  const int x = r >> 6, lr = r & 63;
-  return (lr < 32 ? 0 : kCN / 2 - 32 * kCW) + x * (32 * kCW) + lr * kCW;
+  constexpr int half = kSR / 2;
+  const int x = (int)((unsigned)r / (unsigned)kSR), lr = (int)((unsigned)r % (unsigned)kSR);     // kSR is a power of two
+  return (lr < half ? 0 : kCN / 2 - half * kCW) + x * (half * kCW) + lr * kCW;
 }
 
 // One fluid operator on the slab in z (row layout in, row layout out): row FFT -> spectrum exchange through the
@@ -107,7 +121,7 @@ __device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2
 }
 
 template <int BG, bool LOSS>
-__global__ void __launch_bounds__(kCNT)
+__global__ void __launch_bounds__(kCNT, kCtasPerSM)
 shoot_cluster_kernel(const ClusterParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -147,7 +161,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
     float* m0out = (a.m0 && !a.v0_is_momentum) ? a.m0 + (size_t)p * 2 * N : nullptr;
     const float* m0r = m0s;
     float* uout = a.u + (size_t)p * 2 * N;
-    float* lpart = reinterpret_cast<float*>(bins) + 3 * kMaxSectors;   // 4 x {sq, vm} partials of the loss epilogue
+    float* lpart = reinterpret_cast<float*>(bins) + 3 * kMaxSectors;   // kCL x {sq, vm} partials of the loss epilogue
 
 
     // ---- load v0 (or m0) slab, m0 = flat(v0)
@@ -304,8 +318,10 @@ shoot_cluster_kernel(const ClusterParams prm) {
     }
     cluster.sync();                                     // scratch free for the next pair of this cluster
     if (LOSS && rk == 0 && tid == 0) {
-      a.loss_terms[2 * p] = ((__ldcg(lpart) + __ldcg(lpart + 2)) + __ldcg(lpart + 4)) + __ldcg(lpart + 6);
-      a.loss_terms[2 * p + 1] = ((__ldcg(lpart + 1) + __ldcg(lpart + 3)) + __ldcg(lpart + 5)) + __ldcg(lpart + 7);
+      float sq = 0.f, vm = 0.f;                      // slab partials in fixed order: bitwise reproducible
+      for (int x = 0; x < kCL; ++x) { sq += __ldcg(lpart + 2 * x); vm += __ldcg(lpart + 2 * x + 1); }
+      a.loss_terms[2 * p] = sq;
+      a.loss_terms[2 * p + 1] = vm;
     }
   }
 }
@@ -394,7 +410,7 @@ int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t s
 // operator reuses the consumed dL/du_{s+1} buffer (each CTA writes only its own slab rows of it, see zs_row).
 // Four cluster barriers per adjoint step.
 template <int BG>
-__global__ void __launch_bounds__(kCNT)
+__global__ void __launch_bounds__(kCNT, kCtasPerSM)
 shoot_cluster_bwd_kernel(const ShootBwdParams prm, const int64_t cluster_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
