@@ -94,6 +94,26 @@ __device__ __forceinline__ void init_twiddles(float2* tw, int tid, int nthreads)
   }
 }
 
+#ifndef B2_FFT_GROUPBAR
+#define B2_FFT_GROUPBAR 0
+#endif
+// Barrier between the two radix passes of one 1-D transform.  A line is touched only by the threads with the same
+// (tid % NL), in both passes (NT is a multiple of NL): the warps that share a block of 32 lines form a closed group, so a
+// named barrier over that group (bar.sync id, count) is enough - the groups drift independently instead of all
+// NT threads meeting.  Falls back to __syncthreads() when the lines do not split into whole warps.
+template <int NL, int NT>
+__device__ __forceinline__ void fft_pass_barrier(int tid) {
+#if B2_FFT_GROUPBAR
+  if constexpr (NL % 32 == 0 && NT % NL == 0 && (NL / 32) > 1 && (NL / 32) <= 15) {
+    constexpr int groups = NL / 32, per = NT / groups;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (tid % NL) / 32), "r"(per) : "memory");
+    return;
+  }
+#endif
+  (void)tid;
+  __syncthreads();
+}
+
 // FFTs of length N along element stride `es`, for NL lines spaced `ls` apart.
 // Forward (DIR=-1): natural in -> permuted out.  Inverse (DIR=+1): permuted in ->
 // natural out, unnormalised.  Ends with __syncthreads().
@@ -117,7 +137,7 @@ __device__ __forceinline__ void fft_lines(float2* __restrict__ z, const float2* 
 #pragma unroll
       for (int k1 = 0; k1 < N1; ++k1) base[(N2 * k1) * es] = x[k1];
     }
-    __syncthreads();
+    fft_pass_barrier<NL, NT>(tid);
     for (int t = tid; t < NL * N1; t += NT) {
       const int line = t % NL, k1 = t / NL;
       float2* base = z + line * ls + (N2 * k1) * es;
@@ -143,7 +163,7 @@ __device__ __forceinline__ void fft_lines(float2* __restrict__ z, const float2* 
         base[n2 * es] = (n2 == 0) ? y[n2] : cmul(y[n2], w.x, w.y);
       }
     }
-    __syncthreads();
+    fft_pass_barrier<NL, NT>(tid);
     for (int t = tid; t < NL * N2; t += NT) {
       const int line = t % NL, n2 = t / NL;
       float2* base = z + line * ls + n2 * es;

@@ -159,6 +159,105 @@ splat_fwd_kernel(const float* __restrict__ J, const float* __restrict__ u, float
   }
 }
 
+// ------------------------------------------------------------------ TMA-staged tile variant of the forward gather
+// One CTA = one (pair, band of kTileRows rows).  The rows of I the band can reach - the band plus a halo of
+// kTileHalo rows above and below, full width, i.e. ONE contiguous chunk per channel - are staged in shared memory by
+// the TMA engine (cp.async.bulk global -> shared, completion on an mbarrier; UBLKCP in SASS) while the threads
+// already fetch their displacements.  The four taps of a pixel are then shared-memory reads; a pixel whose 2x2
+// footprint leaves the staged rows (|dt u_0| > halo) falls back to the global gather, so the result is the same
+// for any displacement.  Same taps and same arithmetic as interp_fwd_kernel: bit-identical output.
+#ifndef B2_INTERP_TMA
+#define B2_INTERP_TMA 1
+#endif
+constexpr int kTileThreads = 256;
+constexpr size_t kTileMaxBytes = 48 * 1024;      // per CTA: 4+ CTAs per SM keep enough copies in flight (measured)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B2_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B2_DONE;\n"
+      "bra B2_WAIT;\n"
+      "B2_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int BG, bool ADD_U, int CT>
+__global__ void __launch_bounds__(kTileThreads)
+interp_fwd_tile_kernel(const float* __restrict__ I, const float* __restrict__ u, float* __restrict__ out,
+                       int P, int sI, int gI, int su, int H, int W, int wshift, float dt, int kTileRows, int kTileHalo) {
+  extern __shared__ __align__(128) unsigned char tile_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  float* tile = reinterpret_cast<float*>(tile_raw);
+  const int tid = threadIdx.x, N = H * W;
+  const int r0 = blockIdx.x * kTileRows;
+  const int rlo = max(r0 - kTileHalo, 0), rhi = min(r0 + kTileRows + kTileHalo, H);
+  const int rows = min(kTileRows, H - r0);
+  const int tile_floats = (rhi - rlo) * W;            // per channel
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int p = blockIdx.y; p < P; p += gridDim.y) {
+    const float* Ic = I + (size_t)((p / gI) * sI) * CT * N;
+    if (tid == 0) {
+      mbar_expect_tx(&bar, (uint32_t)(CT * tile_floats * sizeof(float)));
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch)
+        bulk_g2s(tile + ch * tile_floats, Ic + (size_t)ch * N + (size_t)rlo * W, (uint32_t)(tile_floats * sizeof(float)), &bar);
+    }
+    const float* up = u + (size_t)(p * su) * 2 * N + (size_t)r0 * W;
+    float* op = out + (size_t)p * CT * N + (size_t)r0 * W;
+    const int npix = rows * W;
+    // the first displacements are fetched while the bulk copy is in flight
+    float u0n = 0.f, u1n = 0.f;
+    if (tid < npix) { u0n = __ldg(up + tid); u1n = __ldg(up + N + tid); }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    const int lo = rlo * W, hi = rhi * W;
+    for (int x = tid; x < npix; x += kTileThreads) {
+      const float u0 = u0n, u1 = u1n;
+      const int xn = x + kTileThreads;
+      if (xn < npix) { u0n = __ldg(up + xn); u1n = __ldg(up + N + xn); }
+      int r, c;
+      row_col(x, W, wshift, r, c);
+      r += r0;
+      const Taps t = make_taps_fwd<BG>((float)r + dt * u0, (float)c + dt * u1, H, W);
+      const bool inside = t.o00 >= lo && t.o11 < hi;      // o00 / o11 are the smallest / largest of the four offsets
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) {
+        float v;
+        if (inside) {
+          const float* q = tile + ch * tile_floats - lo;
+          v = tap_sample<BG>(t, q[t.o00], q[t.o10], q[t.o01], q[t.o11]);
+        } else {
+          const float* q = Ic + (size_t)ch * N;
+          v = tap_sample<BG>(t, __ldg(q + t.o00), __ldg(q + t.o10), __ldg(q + t.o01), __ldg(q + t.o11));
+        }
+        if (ADD_U) v += dt * (ch == 0 ? u0 : u1);
+        op[(size_t)ch * N + x] = v;
+      }
+    }
+    __syncthreads();      // every thread has finished reading the tile before the next pair's copy overwrites it
+  }
+}
+
 static int log2_or_neg(int64_t W) {
   if (W <= 0 || (W & (W - 1))) return -1;
   int s = 0;
@@ -181,8 +280,40 @@ static dim3 pixel_grid(int64_t P, int64_t N) {
 template <bool ADD_U>
 static int launch_interp_fwd(const float* I, const float* u, float* out, int64_t P, int64_t PI, int64_t Pu,
                              int64_t C, int64_t H, int64_t W, float dt, int bg, cudaStream_t st, int gI = 1) {
-  dim3 grid = pixel_grid(P, H * W);
   const int sI = (PI == P || gI > 1) ? 1 : 0, su = Pu == P ? 1 : 0, ws = log2_or_neg(W);
+  // TMA-staged tiles: 1 or 2 channels, rows that are whole 16-byte units, 16-byte aligned image base; band of 32
+  // rows + 8 halo rows each side, or 16 + 4 when that keeps the tile within kTileMaxBytes
+  int kTileRows = 32, kTileHalo = 8;
+  size_t tile_bytes = sizeof(float) * (size_t)C * (kTileRows + 2 * kTileHalo) * W;
+  if (tile_bytes > kTileMaxBytes) {
+    kTileRows = 16; kTileHalo = 4;
+    tile_bytes = sizeof(float) * (size_t)C * (kTileRows + 2 * kTileHalo) * W;
+  }
+  if (B2_INTERP_TMA && (C == 1 || C == 2) && W % 4 == 0 && H >= kTileRows && tile_bytes <= kTileMaxBytes &&
+      reinterpret_cast<uintptr_t>(I) % 16 == 0) {
+    const int64_t bands = (H + kTileRows - 1) / kTileRows;
+    int64_t gy = P;
+    const int64_t cap = 148 * 32 / bands > 1 ? 148 * 32 / bands : 1;     // a few waves of CTAs; each loops over pairs
+    if (gy > cap) gy = cap;
+    dim3 tgrid((unsigned)bands, (unsigned)gy, 1);
+#define B2_LAUNCH_TILE(BGV, CTV)                                                                                      \
+  do {                                                                                                                \
+    B2_CUDA(cudaFuncSetAttribute(interp_fwd_tile_kernel<BGV, ADD_U, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)tile_bytes));                                                                   \
+    interp_fwd_tile_kernel<BGV, ADD_U, CTV><<<tgrid, kTileThreads, tile_bytes, st>>>(I, u, out, (int)P, sI, gI, su,    \
+                                                                                      (int)H, (int)W, ws, dt,          \
+                                                                                      kTileRows, kTileHalo);           \
+  } while (0)
+    if (bg == B2_BG_CLAMP) {
+      if (C == 1) B2_LAUNCH_TILE(B2_BG_CLAMP, 1); else B2_LAUNCH_TILE(B2_BG_CLAMP, 2);
+    } else {
+      if (C == 1) B2_LAUNCH_TILE(B2_BG_ZERO, 1); else B2_LAUNCH_TILE(B2_BG_ZERO, 2);
+    }
+#undef B2_LAUNCH_TILE
+    B2_CHECK_LAUNCH();
+    return B2_OK;
+  }
+  dim3 grid = pixel_grid(P, H * W);
 #define B2_LAUNCH_FWD(BGV, CTV)                                                                       \
   interp_fwd_kernel<BGV, ADD_U, CTV><<<grid, kThreads, 0, st>>>(I, u, out, (int)P, sI, gI, su, (int)C, \
                                                                (int)H, (int)W, ws, dt)
