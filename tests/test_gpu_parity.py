@@ -30,12 +30,26 @@ def _grads(fn, inputs, gout):
     return out.detach(), [x.grad for x in ins]
 
 
-def _check_op(dev, f_gpu, f_cpu, inputs, seed=100, tol=TOL, gtol=GTOL):
+def _check_op(dev, f_gpu, f_cpu, inputs, seed=100, tol=TOL, gtol=GTOL, kink_aware=False):
+    """Forward and gradients of a GPU op vs the fp32 oracle.  ``kink_aware``: bilinear interpolation is not
+    differentiable where a sample position crosses a grid line; when fp32 rounding puts the oracle and the kernel on
+    different sides of such a kink both gradients are valid but differ at that pixel.  The float64 run of the same
+    oracle tells: a gradient that misses the fp32 oracle must then be within 3x the fp32 oracle's OWN distance from
+    the float64 one."""
     out_c, g_c = _grads(f_cpu, inputs, gout := _rand(*f_cpu(*inputs).shape, seed=seed))
     out_g, g_g = _grads(f_gpu, [x.to(dev) for x in inputs], gout)
     assert relerr(out_g, out_c) < tol, f"forward {relerr(out_g, out_c):.2e}"
+    g_64 = None
     for i, (a, b) in enumerate(zip(g_g, g_c)):
-        assert a is not None and relerr(a, b) < gtol, f"grad[{i}] {relerr(a, b):.2e}"
+        assert a is not None
+        if relerr(a, b) < gtol:
+            continue
+        assert kink_aware, f"grad[{i}] {relerr(a, b):.2e}"
+        if g_64 is None:
+            g_64 = _grads(f_cpu, [x.double() for x in inputs], gout.double())[1]
+        own = relerr(b, g_64[i])
+        assert relerr(a, g_64[i]) < max(gtol, 3.0 * own), \
+            f"grad[{i}] vs fp32 oracle {relerr(a, b):.2e}, vs float64 {relerr(a, g_64[i]):.2e} (oracle32 vs 64: {own:.2e})"
 
 
 @pytest.mark.parametrize("bg", ["clamp", "zero"])
@@ -240,18 +254,28 @@ def test_expmap(pkg, oracle, dev, hw, S):
     assert torch.equal(pkg.expmap(mg, torch.zeros(1, 2, H, W, device=dev), num_steps=2), torch.zeros(1, 2, H, W, device=dev))
 
 
-@pytest.mark.parametrize("H,S", [(16, 5), (32, 5), (64, 4), (128, 3)])
+@pytest.mark.parametrize("H,S", [(16, 5), (32, 5), (64, 4), (128, 3), (256, 2)])
 def test_expmap_adjoint(pkg, oracle, dev, H, S):
     """EPDiff adjoint (b2_shoot_bwd) vs autograd through the oracle, every instantiation of the fused adjoint
-    kernel (<16,16,128>, <32,32,256>, <64,64,256>, <128,128,1024>)."""
+    kernels (<16,16,128>, <32,32,256>, <64,64,256>, <128,128,1024>, the 4-CTA cluster kernel at 256), momentum input."""
     W = H
     mg, mc = pkg.FluidMetric(PARAMS), oracle.FluidMetric(PARAMS)
     m0 = mc.flat(_smooth_v0(pkg, 2, H, W, 22, 2.0))
     _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S), lambda a: oracle.expmap(mc, a, num_steps=S), [m0],
-              gtol=5e-5)
+              gtol=5e-5, kink_aware=True)
     # op-level autograd (EPDiff_step chain) agrees with the fused adjoint
     _check_op(dev, lambda a: pkg.expmap(mg, a, num_steps=S, phiinv=torch.zeros_like(a)),
-              lambda a: oracle.expmap(mc, a, num_steps=S), [m0], gtol=5e-5)
+              lambda a: oracle.expmap(mc, a, num_steps=S), [m0], gtol=5e-5, kink_aware=True)
+    # ... and the three adjoint implementations (fused kernel, op-level sweep, autograd through the op-level chain)
+    # agree with EACH OTHER far below any kink: they sample the same side
+    gout = _rand(2, 2, H, W, seed=100).to(dev)
+    grads = []
+    for mode in ("fused", "sweep"):
+        a = m0.to(dev).requires_grad_(True)
+        with pkg.shooting.force_oplevel(bwd=mode == "sweep"):
+            pkg.expmap(mg, a, num_steps=S).backward(gout)
+        grads.append(a.grad)
+    assert relerr(grads[0], grads[1]) < 5e-5, f"{relerr(grads[0], grads[1]):.2e}"
 
 
 def _masks(pkg, B, T, H, W, seed=2434):
@@ -869,6 +893,33 @@ def test_training_gradient_baseline_grid(pkg, oracle, dev, fused_terms):
                   tar_vol.double(), Sgt.double()).backward()
     own = relerr(vc.grad, vd.grad)
     assert relerr(vg.grad, vd.grad) < max(1e-4, 3 * own), f"vs f64: {relerr(vg.grad, vd.grad):.2e} (oracle32: {own:.2e})"
+
+
+@pytest.mark.parametrize("hw,bg", [((64, 64), "zero"), ((128, 128), "zero"), ((256, 256), "zero"), ((256, 256), "clamp")])
+def test_adjoint_backgrounds_and_explicit_seeds(pkg, oracle, dev, hw, bg):
+    """Fused adjoints with explicit gradient seeds (dL/du, dL/dvel, dL/dm0 as tensors: the unfused loss path) under
+    both background rules, with a velocity large enough to sample outside the grid, vs autograd through the oracle."""
+    H, W = hw
+    B, T, S = 1, 3, 3
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 88, 6.0)
+    conv = oracle.Conventions(background=bg)
+    wu, wv, wm = _rand(2, 2, H, W, seed=1), _rand(2, 2, H, W, seed=2), _rand(2, 2, H, W, seed=3)
+
+    def loss(out, tarv, wu, wv, wm):
+        return (out["displacement"] * wu).sum() + (out["velocity"] * wv).sum() + 0.01 * (out["momentum"] * wm).sum() \
+            + ((tarv - out["deformed_source"]) ** 2).sum() + 100.0 * (out["strain_matrix"] ** 2).sum()
+
+    vc = v0.clone().requires_grad_(True)
+    loss(oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, conv=conv), tar_vol, wu, wv, wm).backward()
+    vd = v0.double().requires_grad_(True)
+    loss(oracle.forward_volume(vd, src_vol.double(), tar_vol.double(), oracle.FluidMetric(PARAMS), S, conv=conv),
+         tar_vol.double(), wu.double(), wv.double(), wm.double()).backward()
+    own = relerr(vc.grad, vd.grad)
+    vg = v0.to(dev).requires_grad_(True)
+    out = pkg.shoot_warp_strain(vg, src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S, background=bg)
+    loss(out, tar_vol.to(dev), wu.to(dev), wv.to(dev), wm.to(dev)).backward()
+    assert relerr(vg.grad, vd.grad) < max(1e-4, 3 * own), f"{relerr(vg.grad, vd.grad):.2e} (oracle32 vs 64: {own:.2e})"
 
 
 def test_training_gradient_256_fused_adjoint(pkg, oracle, dev):
