@@ -256,6 +256,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:
+        all_cpus = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        all_cpus = None
     bind_to_gpu_numa_node(local)         # pinned staging memory is first-touched on the GPU's NUMA node
     dist = None
     if world > 1:
@@ -433,6 +437,8 @@ def main():
         if extra is not None:
             line["extra"] = extra
         if n == 1 and not args.no_cpu_baseline:
+            if all_cpus:                                 # the CPU baseline gets every host core again
+                os.sched_setaffinity(0, all_cpus)
             cpu_v, what, threads = cpu_pairs_per_s(pkg, args.cpu_sample_slices, 3)
             line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_sample_slices} slices x {T1} pairs of the same workload, "
