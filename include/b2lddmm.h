@@ -247,6 +247,25 @@ typedef struct b2_shoot_bwd_args {
   int64_t P, H, W;
   int32_t num_steps, background, v0_is_momentum, flags;
   float alpha, beta, gamma, T;
+  /* Optional fused seeds of dL/du^S (single-CTA adjoint, square grids up to 128x128; B2_E_PARAM elsewhere - run
+   * b2_strain_sector_bwd_ex / b2_warp_sqerr_bwd and pass `gu` instead): the adjoint of the strain-matrix reduction
+   * (seed_gS = dL/dS (B,1,n_sectors,n_frames), with the forward's counts, moments and sector frame) and of the squared
+   * error sum_x (tar - interp(src, u^S))^2 (seed_g_sq (P) = its upstream gradient per pair) are taken in the prologue
+   * of the adjoint kernel from u^S, src and tar (addressing as in b2_shoot_args), added to `gu` when that is given.
+   * No (P,2,H,W) gradient image, no extra launches. */
+  const float* seed_gS;
+  const int32_t* seed_counts;
+  const int64_t* seed_moments;
+  const int32_t* seed_table;
+  int64_t seed_table_slice_stride;
+  const float* seed_theta0;
+  const int32_t* seed_clockwise;
+  const float* seed_g_sq;
+  const float* seed_u;
+  const float* seed_src;
+  const float* seed_tar;
+  int64_t seed_T1, seed_src_slice_stride, seed_tar_slice_stride;
+  int32_t seed_n_sectors, seed_n_frames, seed_src_per_pair, seed_reserved_;
 } b2_shoot_bwd_args;
 int64_t b2_sizeof_shoot_bwd_args(void);
 int64_t b2_shoot_bwd_workspace_bytes_flags(int64_t P, int64_t H, int64_t W, int flags);

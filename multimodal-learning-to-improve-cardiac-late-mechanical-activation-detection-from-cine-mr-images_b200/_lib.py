@@ -54,6 +54,12 @@ class ShootBwdArgs(C.Structure):
         ("P", C.c_int64), ("H", C.c_int64), ("W", C.c_int64),
         ("num_steps", C.c_int32), ("background", C.c_int32), ("v0_is_momentum", C.c_int32), ("flags", C.c_int32),
         ("alpha", C.c_float), ("beta", C.c_float), ("gamma", C.c_float), ("T", C.c_float),
+        ("seed_gS", C.c_void_p), ("seed_counts", C.c_void_p), ("seed_moments", C.c_void_p), ("seed_table", C.c_void_p),
+        ("seed_table_slice_stride", C.c_int64), ("seed_theta0", C.c_void_p), ("seed_clockwise", C.c_void_p),
+        ("seed_g_sq", C.c_void_p), ("seed_u", C.c_void_p), ("seed_src", C.c_void_p), ("seed_tar", C.c_void_p),
+        ("seed_T1", C.c_int64), ("seed_src_slice_stride", C.c_int64), ("seed_tar_slice_stride", C.c_int64),
+        ("seed_n_sectors", C.c_int32), ("seed_n_frames", C.c_int32), ("seed_src_per_pair", C.c_int32),
+        ("seed_reserved_", C.c_int32),
     ]
 
 

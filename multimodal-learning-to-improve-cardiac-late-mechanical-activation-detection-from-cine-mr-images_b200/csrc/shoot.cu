@@ -382,6 +382,13 @@ __device__ __forceinline__ void prefetch_traj_l2(const float* us, const float* v
 #endif
 }
 
+// shared memory of the adjoint kernel: field + LUTs, then the seed prologue's sector table and weights
+template <int H, int W>
+struct BwdSmem {
+  static constexpr size_t seed_off = (FluidSmem<H, W>::bytes + 15) & ~size_t(15);
+  static constexpr size_t bytes = seed_off + sizeof(int32_t) * 3 * kFusedMaxSectors;
+};
+
 // ------------------------------------------------------------------ fused EPDiff adjoint (path A)
 // Reverse sweep over the saved trajectory, one CTA per frame-pair at a time, same residency scheme as the
 // forward: dL/dv_s -> dL/dm_s lives in shared memory (the self-adjoint sharp is the in-SM FFT), the gradient
@@ -416,6 +423,9 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
   float* Ga = prm.scratch + (size_t)blockIdx.x * 3 * prm.field;
   float* Gb = Ga + prm.field;
   float* A = Gb + prm.field;
+  const BwdSeed& sd = prm.seed;
+  int32_t* tab_s = reinterpret_cast<int32_t*>(smem_raw + BwdSmem<H, W>::seed_off);      // seeds: sector table
+  float* gk_s = reinterpret_cast<float*>(tab_s + 2 * kFusedMaxSectors);                   //        + per-sector weights
   __syncthreads();
 
   for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
@@ -428,6 +438,41 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       Gcur[N + i] = prm.gu ? __ldg(prm.gu + (size_t)p * prm.field + N + i) : 0.f;
       A[i] = prm.gm0 ? __ldg(prm.gm0 + (size_t)p * prm.field + i) : 0.f;
       A[N + i] = prm.gm0 ? __ldg(prm.gm0 + (size_t)p * prm.field + N + i) : 0.f;
+    }
+    if (sd.gS || sd.g_sq) {
+      // ---- seeds of dL/du^S taken here instead of by two kernels through a gradient image: the adjoint of the
+      // strain-matrix reduction (REDs of the member pixels' stencils into the accumulator) and of the squared
+      // error of the warped source (own pixel, recomputed from the taps of src at x + u^S)
+      const int64_t b = p / sd.T1;
+      const int t = (int)(p % sd.T1);
+      const float* uS = sd.uS + (size_t)p * prm.field;
+      const float* tarp = sd.tar_slice_stride ? sd.tar + (size_t)b * sd.tar_slice_stride + (size_t)t * N
+                                              : sd.tar + (size_t)p * N;
+      if (sd.gS) {
+        const SectorFrame sf = sector_frame_of(sd.table, sd.table_slice_stride, sd.theta0, sd.clockwise, b);
+        for (int i = tid; i < 2 * sd.n_sectors; i += NT) tab_s[i] = sf.table[i];
+        strain_bwd_weights<NT>(sd.gS, sd.counts, (int)b, t, (int)sd.T1, sd.n_sectors, sd.n_frames, gk_s, tid);
+        __syncthreads();            // accumulator seeded, table and weights visible
+        strain_bwd_frame<NT>(uS, uS + N, tarp, sd.moments + 3 * b, tab_s, sd.n_sectors, H, W, gk_s, Gcur, Gcur + N, tid,
+                             sf.theta0, sf.flip);
+      }
+      if (sd.g_sq) {
+        const float* srcp = sd.src_per_pair
+                                ? (sd.src_slice_stride ? sd.src + (size_t)b * sd.src_slice_stride + (size_t)t * N
+                                                       : sd.src + (size_t)p * N)
+                                : sd.src + (size_t)b * (sd.src_slice_stride ? sd.src_slice_stride : N);
+        const float g2 = 2.f * __ldg(sd.g_sq + p);
+        for (int k = 0; k < NB; ++k) {
+          const int r = rbase + k, i = r * W + c;
+          const Taps tp = make_taps<BG>((float)r + __ldg(uS + i), (float)c + __ldg(uS + N + i), H, W);
+          const float v00 = __ldg(srcp + tp.o00), v10 = __ldg(srcp + tp.o10), v01 = __ldg(srcp + tp.o01), v11 = __ldg(srcp + tp.o11);
+          const float g = g2 * (tap_sample<BG>(tp, v00, v10, v01, v11) - __ldg(tarp + i));
+          float a0, a1;
+          tap_grad<BG>(tp, v00, v10, v01, v11, a0, a1);
+          atomicAdd(Gcur + i, g * a0);       // RED: the strain adjoint of neighbouring pixels may target this pixel too
+          atomicAdd(Gcur + N + i, g * a1);
+        }
+      }
     }
     __syncthreads();
 
@@ -624,7 +669,7 @@ template <int H, int W, int NT>
 static int bwd_ctas_per_sm() {
   static int cached = 0;
   if (cached) return cached;
-  const size_t smem = FluidSmem<H, W>::bytes;
+  const size_t smem = BwdSmem<H, W>::bytes;
   int per = 0;
   if (cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
           cudaSuccess ||
@@ -654,7 +699,7 @@ static int64_t fused_bwd_grid(int64_t P, int64_t H) {
 
 template <int H, int W, int NT>
 static int launch_fused_bwd(const ShootBwdParams& prm, int background, cudaStream_t st) {
-  const size_t smem = FluidSmem<H, W>::bytes;
+  const size_t smem = BwdSmem<H, W>::bytes;
   const int64_t grid = fused_bwd_grid(prm.P, H);
   if (background == B2_BG_CLAMP) {
     B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -833,8 +878,11 @@ extern "C" int b2_shoot_bwd_loss(const float* gu, const float* gvel, const float
                                  const float* m0, const float* traj, float* gv0, int64_t P, int64_t H, int64_t W,
                                  int num_steps, float alpha, float beta, float gamma, float T, int background,
                                  int v0_is_momentum, void* workspace, int64_t workspace_bytes, void* stream) {
-  const b2_shoot_bwd_args a{gu, gvel, gm0, g_reg, m0, traj, gv0, P, H, W, num_steps, background, v0_is_momentum, 0,
-                            alpha, beta, gamma, T};
+  b2_shoot_bwd_args a = {};
+  a.gu = gu; a.gvel = gvel; a.gm0 = gm0; a.g_reg = g_reg; a.m0 = m0; a.traj = traj; a.gv0 = gv0;
+  a.P = P; a.H = H; a.W = W;
+  a.num_steps = num_steps; a.background = background; a.v0_is_momentum = v0_is_momentum; a.flags = 0;
+  a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.T = T;
   return b2_shoot_bwd_ex(&a, workspace, workspace_bytes, stream);
 }
 
@@ -856,7 +904,21 @@ extern "C" int b2_shoot_bwd_ex(const b2_shoot_bwd_args* args, void* workspace, i
   if (fused_size(H, W, args->flags) || cluster_bwd_size(H, W, P, args->flags)) {
     // fused adjoint: one persistent kernel; scratch = resident CTAs (clusters) x 3 fields
     ShootBwdParams prm{gu, gvel, gm0, g_reg, m0, traj, gv0, reinterpret_cast<float*>(workspace), P, 2 * H * W,
-                       num_steps, v0_is_momentum, alpha, beta, gamma, T};
+                       num_steps, v0_is_momentum, alpha, beta, gamma, T, {}};
+    if (args->seed_gS || args->seed_g_sq) {
+      // fused seeds: single-CTA adjoint only (the caller runs the two seed kernels itself on the other paths)
+      if (H > 128) return B2_E_PARAM;
+      if (!args->seed_u || !args->seed_tar || args->seed_T1 <= 0 || P % args->seed_T1 != 0) return B2_E_NULL;
+      if (args->seed_gS && (!args->seed_counts || !args->seed_moments || !args->seed_table || args->seed_n_sectors < 3 ||
+                            args->seed_n_sectors > kFusedMaxSectors || args->seed_n_frames < 1 || args->seed_table_slice_stride < 0))
+        return B2_E_PARAM;
+      if (args->seed_g_sq && !args->seed_src) return B2_E_NULL;
+      prm.seed = BwdSeed{args->seed_gS, args->seed_counts, reinterpret_cast<const long long*>(args->seed_moments),
+                         args->seed_table, args->seed_table_slice_stride, args->seed_theta0, args->seed_clockwise,
+                         args->seed_g_sq, args->seed_u, args->seed_src, args->seed_tar, args->seed_T1,
+                         args->seed_src_slice_stride, args->seed_tar_slice_stride, args->seed_n_sectors,
+                         args->seed_n_frames, args->seed_src_per_pair};
+    }
     switch ((int)H) {
       case 16: return launch_fused_bwd<16, 16, 128>(prm, background, st);
       case 32: return launch_fused_bwd<32, 32, 256>(prm, background, st);
@@ -865,6 +927,7 @@ extern "C" int b2_shoot_bwd_ex(const b2_shoot_bwd_args* args, void* workspace, i
       case 256: return launch_shoot_cluster_bwd(prm, background, st);
     }
   }
+  if (args->seed_gS || args->seed_g_sq) return B2_E_PARAM;     // fused seeds exist in the single-CTA adjoint only
   const size_t n = (size_t)P * 2 * H * W, fbytes = align256(sizeof(float) * n);
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   float* g_u = reinterpret_cast<float*>(ws);                  // dL/du_{s+1}

@@ -4,6 +4,25 @@
 
 namespace b2 {
 
+// Optional seeds of dL/du^S computed in the prologue of the fused adjoint kernel instead of by separate kernels
+// (b2_strain_sector_bwd_ex + b2_warp_sqerr_bwd) through a (P,2,H,W) gradient image: the adjoint of the strain-matrix
+// reduction (gS != nullptr) and of the squared-error term of the reconstruction loss (g_sq != nullptr).
+struct BwdSeed {
+  const float* gS;            // (B,1,n_sectors,n_frames) dL/dS
+  const int32_t* counts;      // (B,n_sectors,T1) member counts of the forward
+  const long long* moments;   // (B,3)
+  const int32_t* table;       // sector frame (b2_sector_frame)
+  long long table_slice_stride;
+  const float* theta0;
+  const int32_t* clockwise;
+  const float* g_sq;          // (P) dL/d(sum (tar - Sdef)^2)
+  const float* uS;            // (P,2,H,W) final displacement u^S
+  const float* src;
+  const float* tar;
+  long long T1, src_slice_stride, tar_slice_stride;
+  int n_sectors, n_frames, src_per_pair;
+};
+
 // Fused EPDiff adjoint (reverse sweep over the saved trajectory, b2_shoot_bwd_ex)
 struct ShootBwdParams {
   const float* gu;      // dL/du^S   (P,2,H,W) or nullptr
@@ -18,6 +37,7 @@ struct ShootBwdParams {
   int64_t P, field;
   int num_steps, v0_is_momentum;
   float alpha, beta, gamma, T;
+  BwdSeed seed;         // all-null = none
 };
 
 }  // namespace b2

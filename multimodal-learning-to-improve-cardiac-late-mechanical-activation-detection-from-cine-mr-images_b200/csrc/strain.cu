@@ -88,61 +88,12 @@ strain_sector_bwd_kernel(const float* __restrict__ gS, const float* __restrict__
     const SectorFrame f = sector_frame_of(fr.table, fr.table_slice_stride, fr.theta0, fr.clockwise, b);
     __syncthreads();
     for (int i = tid; i < 2 * n_sectors; i += kNTS) tab_s[i] = f.table[i];
-    for (int k = tid; k < n_sectors; k += kNTS) {
-      const float* row = gS + ((size_t)b * n_sectors + k) * n_frames;
-      float g = (t < n_frames) ? row[t] : 0.f;
-      if (t == T1 - 1)
-        for (int tt = T1; tt < n_frames; ++tt) g += row[tt];
-      const int cn = counts[((size_t)b * n_sectors + k) * T1 + t];
-      gk_s[k] = g / (float)max(cn, 1);
-    }
+    strain_bwd_weights<kNTS>(gS, counts, b, t, T1, n_sectors, n_frames, gk_s, tid);
     __syncthreads();
-    const long long* mo = mom + 3 * b;
-    const long long cnt = mo[0], sx = mo[1], sy = mo[2];
-    float c0, c1;
-    centroid_from_moments(mo, H, W, c0, c1);
     const float* u0 = u + (size_t)pt * 2 * N;
-    const float* u1 = u0 + N;
-    const float* mask = tar + (size_t)pt * N;
     float* d0 = du + (size_t)pt * 2 * N;
-    float* d1 = d0 + N;
-    for (int x = tid; x < N; x += kNTS) {
-      if (!(mask[x] > 0.5f)) continue;
-      const int r = x / W, c = x - r * W;
-      const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors, f.theta0, f.flip);
-      if (k < 0) continue;
-      int rlo, rhi, clo, chi; float sr, sc;
-      diff_idx(r, H, rlo, rhi, sr);
-      diff_idx(c, W, clo, chi, sc);
-      const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
-      const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
-      const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
-      const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
-      EccTerms e; float ecc;
-      if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[x], (float)c + u1[x], c0, c1, e, ecc)) continue;
-      const float gq = 0.5f * gk_s[k];
-      if (gq == 0.f) continue;
-      const float e0 = -e.n1, e1 = e.n0;
-      const float g_t0 = gq * 2.f * e.t0 / e.den, g_t1 = gq * 2.f * e.t1 / e.den;
-      const float g_den = -gq * e.q / e.den;
-      const float g_rad2 = g_den * e.det * e.det;
-      const float g_det = g_den * e.rad2 * 2.f * e.det;
-      float g_G11 = g_t0 * e0 + g_det * e.G00;
-      float g_G01 = -g_t0 * e1 - g_det * e.G10;
-      float g_G00 = g_t1 * e1 + g_det * e.G11;
-      float g_G10 = -g_t1 * e0 - g_det * e.G01;
-      const float g_e0 = g_t0 * e.G11 - g_t1 * e.G10;
-      const float g_e1 = -g_t0 * e.G01 + g_t1 * e.G00;
-      const float g_n0 = 2.f * e.n0 * g_rad2 + g_e1;
-      const float g_n1 = 2.f * e.n1 * g_rad2 - g_e0;
-      atomicAdd(d0 + x, g_n0);
-      atomicAdd(d1 + x, g_n1);
-      // G00 = 1 + d0 u0, G10 = d0 u1 (row differences); G01 = d1 u0, G11 = 1 + d1 u1 (col differences)
-      atomicAdd(d0 + rhi * W + c, sr * g_G00); atomicAdd(d0 + rlo * W + c, -sr * g_G00);
-      atomicAdd(d1 + rhi * W + c, sr * g_G10); atomicAdd(d1 + rlo * W + c, -sr * g_G10);
-      atomicAdd(d0 + r * W + chi, sc * g_G01); atomicAdd(d0 + r * W + clo, -sc * g_G01);
-      atomicAdd(d1 + r * W + chi, sc * g_G11); atomicAdd(d1 + r * W + clo, -sc * g_G11);
-    }
+    strain_bwd_frame<kNTS>(u0, u0 + N, tar + (size_t)pt * N, mom + 3 * b, tab_s, n_sectors, H, W, gk_s, d0, d0 + N, tid,
+                           f.theta0, f.flip);
   }
 }
 

@@ -52,6 +52,70 @@ __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u
   __syncthreads();
 }
 
+// ---- adjoint of the reduction (shared by strain_sector_bwd_kernel and the prologue of the fused EPDiff adjoint)
+// dL/dEcc of a member pixel of sector k of pair (b, t): (gS[b,k,t] + the edge-padded columns of the last frame) / count
+template <int NT>
+__device__ __forceinline__ void strain_bwd_weights(const float* __restrict__ gS, const int32_t* __restrict__ counts, int b,
+                                                   int t, int T1, int n_sectors, int n_frames, float* gk_s, int tid) {
+  for (int k = tid; k < n_sectors; k += NT) {
+    const float* row = gS + ((size_t)b * n_sectors + k) * n_frames;
+    float g = (t < n_frames) ? row[t] : 0.f;
+    if (t == T1 - 1)
+      for (int tt = T1; tt < n_frames; ++tt) g += row[tt];
+    const int cn = counts[((size_t)b * n_sectors + k) * T1 + t];
+    gk_s[k] = g / (float)max(cn, 1);
+  }
+}
+
+// Accumulates dL/du of one pair into d0 / d1 with float atomics (d zero- or seed-filled by the caller, complete
+// before the call; gk_s and tab_s visible to the CTA).  All threads of the CTA call this.
+template <int NT>
+__device__ __forceinline__ void strain_bwd_frame(const float* u0, const float* u1, const float* __restrict__ mask,
+                                                 const long long* mom, const int32_t* tab_s, int n_sectors, int H, int W,
+                                                 const float* gk_s, float* d0, float* d1, int tid, float theta0, bool flip) {
+  const long long cnt = mom[0], sx = mom[1], sy = mom[2];
+  float c0, c1;
+  centroid_from_moments(mom, H, W, c0, c1);
+  const int N = H * W;
+  for (int x = tid; x < N; x += NT) {
+    if (!(mask[x] > 0.5f)) continue;
+    const int r = x / W, c = x - r * W;
+    const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors, theta0, flip);
+    if (k < 0) continue;
+    int rlo, rhi, clo, chi; float sr, sc;
+    diff_idx(r, H, rlo, rhi, sr);
+    diff_idx(c, W, clo, chi, sc);
+    const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
+    const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+    const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
+    const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+    EccTerms e; float ecc;
+    if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[x], (float)c + u1[x], c0, c1, e, ecc)) continue;
+    const float gq = 0.5f * gk_s[k];
+    if (gq == 0.f) continue;
+    const float e0 = -e.n1, e1 = e.n0;
+    const float g_t0 = gq * 2.f * e.t0 / e.den, g_t1 = gq * 2.f * e.t1 / e.den;
+    const float g_den = -gq * e.q / e.den;
+    const float g_rad2 = g_den * e.det * e.det;
+    const float g_det = g_den * e.rad2 * 2.f * e.det;
+    float g_G11 = g_t0 * e0 + g_det * e.G00;
+    float g_G01 = -g_t0 * e1 - g_det * e.G10;
+    float g_G00 = g_t1 * e1 + g_det * e.G11;
+    float g_G10 = -g_t1 * e0 - g_det * e.G01;
+    const float g_e0 = g_t0 * e.G11 - g_t1 * e.G10;
+    const float g_e1 = -g_t0 * e.G01 + g_t1 * e.G00;
+    const float g_n0 = 2.f * e.n0 * g_rad2 + g_e1;
+    const float g_n1 = 2.f * e.n1 * g_rad2 - g_e0;
+    atomicAdd(d0 + x, g_n0);
+    atomicAdd(d1 + x, g_n1);
+    // G00 = 1 + d0 u0, G10 = d0 u1 (row differences); G01 = d1 u0, G11 = 1 + d1 u1 (col differences)
+    atomicAdd(d0 + rhi * W + c, sr * g_G00); atomicAdd(d0 + rlo * W + c, -sr * g_G00);
+    atomicAdd(d1 + rhi * W + c, sr * g_G10); atomicAdd(d1 + rlo * W + c, -sr * g_G10);
+    atomicAdd(d0 + r * W + chi, sc * g_G01); atomicAdd(d0 + r * W + clo, -sc * g_G01);
+    atomicAdd(d1 + r * W + chi, sc * g_G11); atomicAdd(d1 + r * W + clo, -sc * g_G11);
+  }
+}
+
 // Write column t of S (B,1,K,n_frames) from the bins, with edge-padding of the
 // last frame and cropping beyond n_frames (align_n_frames_to semantics).
 template <int NT>

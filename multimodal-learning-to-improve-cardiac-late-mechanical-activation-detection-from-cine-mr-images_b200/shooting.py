@@ -25,6 +25,10 @@ from .strain import N_SECTORS, Frame, mask_moments
 # kernels are the default wherever they exist; `force_oplevel` selects the op-level kernel sequence (path B) for
 # A/B comparisons and tests.  No environment variable is read.
 _flags = {"fwd": 0, "bwd": 0}
+# The seeds of dL/du^S (adjoint of the strain-matrix reduction and of the squared-error term) are taken in the prologue
+# of the fused adjoint kernel where that exists (square grids up to 128x128); False runs them as separate kernels
+# through a gradient image (always the case at 256x256, on the op-level path, or when dL/dsrc is wanted).
+fuse_seeds = True
 
 
 @contextlib.contextmanager
@@ -107,7 +111,8 @@ def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background
     return out
 
 
-def _shoot_bwd(gu, gvel, gm0, m0, traj, metric, num_steps, T, background, v0_is_momentum, g_reg=None):
+def _shoot_bwd(gu, gvel, gm0, m0, traj, metric, num_steps, T, background, v0_is_momentum, g_reg=None, seeds=None):
+    """``seeds``: dict of the fused-seed fields of ``b2_shoot_bwd_args`` (tensors / ints) or None."""
     P, _, H, W = m0.shape
     gv0 = torch.empty_like(m0)
     a = ShootBwdArgs()
@@ -116,6 +121,8 @@ def _shoot_bwd(gu, gvel, gm0, m0, traj, metric, num_steps, T, background, v0_is_
     a.P, a.H, a.W = P, H, W
     a.num_steps, a.background, a.v0_is_momentum, a.flags = int(num_steps), int(background), int(v0_is_momentum), _flags["bwd"]
     a.alpha, a.beta, a.gamma, a.T = metric.alpha, metric.beta, metric.gamma, float(T)
+    for k, v in (seeds or {}).items():
+        setattr(a, "seed_" + k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
     nbytes = lib().b2_shoot_bwd_workspace_bytes_flags(P, H, W, a.flags)       # sized per path (fused: resident CTAs)
     if nbytes <= 0:
         check(-4, "b2_shoot_bwd_workspace_bytes")
@@ -230,7 +237,21 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         def add(acc, x):
             return x if acc is None else acc.add_(x)
 
-        if with_strain and gS is not None:
+        # seeds of dL/du^S inside the adjoint kernel (no gradient image, no extra launches) where it has the prologue
+        seeds = None
+        fused_seeds = (fuse_seeds and ctx.needs_input_grad[0] and not want_dsrc and _fused_bwd_size(H, W) and H <= 128
+                       and ((with_strain and gS is not None) or glt is not None))
+        keep = []              # tensors that must outlive the launch
+        if fused_seeds:
+            seeds = {"u": u, "tar": tar, "T1": T1, "tar_slice_stride": int(tar_ss)}
+            if with_strain and gS is not None:
+                gS_c = gS.contiguous()
+                keep.append(gS_c)
+                fs = ctx.frame.c_struct()
+                seeds.update({"gS": gS_c, "counts": counts, "moments": moments, "table": fs.table,
+                              "table_slice_stride": fs.table_slice_stride, "theta0": fs.theta0, "clockwise": fs.clockwise,
+                              "n_sectors": n_sectors, "n_frames": n_frames})
+        elif with_strain and gS is not None:
             du = torch.empty_like(u)
             tar_c = tar.reshape(B, T1, H, W).contiguous()
             gS_c = gS.contiguous()          # named: a temporary would be freed before the launch is enqueued
@@ -246,15 +267,19 @@ class ShootWarpStrainFunction(torch.autograd.Function):
             # read in place - and the closed-form regularisation gradient inside the adjoint kernel (g_reg)
             g_sq = glt[:, 0].contiguous()
             g_reg = glt[:, 1].contiguous()
-            acc = gu_tot is not None
-            if not acc:
-                gu_tot = torch.empty_like(u)
-            d2 = torch.empty((P if src_per_pair else B, 1, H, W), device=u.device) if want_dsrc else None
-            check(lib().b2_warp_sqerr_bwd(ptr(g_sq), ptr(src), ptr(tar), ptr(u), ptr(gu_tot), ptr(d2), B, T1, H, W,
-                                          int(src_per_pair), int(src_ss), int(tar_ss), background, int(acc), stream()),
-                  "b2_warp_sqerr_bwd")
-            _lib.count_launch()
-            dsrc = add(dsrc, d2) if d2 is not None else dsrc
+            if fused_seeds:
+                keep.append(g_sq)
+                seeds.update({"g_sq": g_sq, "src": src, "src_slice_stride": int(src_ss), "src_per_pair": int(src_per_pair)})
+            else:
+                acc = gu_tot is not None
+                if not acc:
+                    gu_tot = torch.empty_like(u)
+                d2 = torch.empty((P if src_per_pair else B, 1, H, W), device=u.device) if want_dsrc else None
+                check(lib().b2_warp_sqerr_bwd(ptr(g_sq), ptr(src), ptr(tar), ptr(u), ptr(gu_tot), ptr(d2), B, T1, H, W,
+                                              int(src_per_pair), int(src_ss), int(tar_ss), background, int(acc), stream()),
+                      "b2_warp_sqerr_bwd")
+                _lib.count_launch()
+                dsrc = add(dsrc, d2) if d2 is not None else dsrc
         if gsdef is not None:
             # op-level adjoint kernels take dense batches
             src_c = src.reshape(P, 1, H, W).contiguous() if src_per_pair else src.contiguous()
@@ -276,7 +301,7 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gv0 = _shoot_bwd(gu_tot, gvel.contiguous() if gvel is not None else None,
                              gm0.contiguous() if gm0 is not None else None, m0, traj, metric, num_steps, T,
-                             background, False, g_reg=g_reg)
+                             background, False, g_reg=g_reg, seeds=seeds)
         if dsrc is not None:
             dsrc = dsrc.reshape(src.shape)
         return (gv0, dsrc) + (None,) * 16

@@ -1248,3 +1248,44 @@ def test_guard_bands_around_every_buffer(pkg, dev, cfg):
     for k in ("m0", "traj"):                                   # read-only inputs of the adjoint are left as they were
         assert intact(bufs[k][0], bufs[k][1].numel())
     assert lib.b2_shoot_bwd_ex(C.byref(b), L.ptr(bws), nbw - 1, L.stream()) == -6
+
+
+@pytest.mark.parametrize("cfg", [(2, 4, 32, 32, 4, "Lagrangian"), (2, 3, 64, 64, 3, "Eulerian"), (1, 4, 128, 128, 5, "Lagrangian")])
+def test_fused_seeds_match_seed_kernels(pkg, oracle, dev, cfg):
+    """The seeds of dL/du^S taken in the prologue of the fused adjoint kernel (strain-matrix adjoint + squared-error
+    adjoint, b2_shoot_bwd_args.seed_*) against the same gradient through the separate seed kernels and a gradient
+    image, with and without the loss epilogue, in a rotated sector frame; and against autograd through the oracle."""
+    B, T, H, W, S, split = cfg
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    src_vol, tar_vol = oracle.split_vol_to_registration_pairs(vol, split, 3)
+    v0 = _smooth_v0(pkg, B * (T - 1), H, W, 47, 2.5)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=48)
+    th, cw = [0.4 + b for b in range(B)], [b % 2 == 0 for b in range(B)]
+    vc = v0.clone().requires_grad_(True)
+    oc = oracle.forward_volume(vc, src_vol, tar_vol, oracle.FluidMetric(PARAMS), S, theta0=th, clockwise=cw)
+    _trainer_loss(oc, tar_vol, Sgt).backward()
+    # float64 ground truth: the warped image is a BINARY mask, so the squared-error gradient has kinks wherever a
+    # sample position crosses a grid line - the fp32 oracle's own distance from float64 bounds what can be asked
+    vd = v0.double().requires_grad_(True)
+    od = oracle.forward_volume(vd, src_vol.double(), tar_vol.double(), oracle.FluidMetric(PARAMS), S, theta0=th, clockwise=cw)
+    _trainer_loss(od, tar_vol.double(), Sgt.double()).backward()
+    own = relerr(vc.grad, vd.grad)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol.to(dev), split, 3)
+    crit = pkg.RegistrationReconstructionLoss(0.03, 0.1)
+    for loss_terms in (True, False):
+        grads = {}
+        for fused in (True, False):
+            pkg.shooting.fuse_seeds = fused
+            try:
+                vg = v0.to(dev).requires_grad_(True)
+                l0 = pkg._lib.launches()
+                out = pkg.shoot_warp_strain(vg, sv, tv, pkg.FluidMetric(PARAMS), num_steps=S, loss_terms=loss_terms,
+                                            theta0=th, clockwise=cw)
+                _trainer_loss(out, tv, Sgt.to(dev), crit).backward()
+                grads[fused] = (vg.grad, pkg._lib.launches() - l0)
+            finally:
+                pkg.shooting.fuse_seeds = True
+            assert relerr(vg.grad, vd.grad) < max(1e-4, 3 * own), \
+                f"fused={fused} loss_terms={loss_terms}: {relerr(vg.grad, vd.grad):.2e} (oracle32 vs 64: {own:.2e})"
+        assert relerr(grads[True][0], grads[False][0]) < 5e-5, f"{relerr(grads[True][0], grads[False][0]):.2e}"
+        assert grads[True][1] < grads[False][1]              # fewer launches of our kernels
