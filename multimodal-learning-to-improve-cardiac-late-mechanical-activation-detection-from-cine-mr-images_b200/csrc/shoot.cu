@@ -361,6 +361,29 @@ constexpr int kBwdUnrollB1 = B2_BWD_U1, kBwdUnrollB3a = B2_BWD_U3A, kBwdUnrollB3
                           // (configs[2] training step: off 11.84 ms, 2: 11.61, 4: 11.66, 8: 11.62)
 #endif
 
+#ifndef B2_BWD_EVICT_FIRST
+#define B2_BWD_EVICT_FIRST 0
+#endif
+// Trajectory loads of the adjoint with an L2 evict-first policy (createpolicy + ld.global.nc.L2::cache_hint): the
+// (u_s, v_s) entry streams through once per step, the scratch fields and m0 are what should stay in L2.
+__device__ __forceinline__ unsigned long long make_evict_first_policy() {
+  unsigned long long pol = 0;
+#if B2_BWD_EVICT_FIRST
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+__device__ __forceinline__ float ldg_stream(const float* p, unsigned long long pol) {
+#if B2_BWD_EVICT_FIRST
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol;
+  return __ldg(p);
+#endif
+}
+
 // L2 prefetch of one (u_s, v_s) trajectory entry (2 fields): the adjoint's first phase of a step touches them for
 // the first time (HBM latency on a dependent load chain); issued one phase earlier they arrive in L2 in time.
 // Variant 1: one prefetch.global.L2 per 128-byte line, spread over the CTA; variant 2: four bulk prefetches.
@@ -420,6 +443,7 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
   const float cmc = (c >= 1) ? diff_scale(c - 1, W) : 0.f, cpc = (c <= W - 2) ? diff_scale(c + 1, W) : 0.f;
   const float c0c = (c == W - 1 ? 1.f : 0.f) - (c == 0 ? 1.f : 0.f);
   FS::init_luts(twH, twW, csH, csW, tid, NT);
+  const unsigned long long pol = make_evict_first_policy();
   float* Ga = prm.scratch + (size_t)blockIdx.x * 3 * prm.field;
   float* Gb = Ga + prm.field;
   float* A = Gb + prm.field;
@@ -499,8 +523,8 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
 #pragma unroll
         for (int j = 0; j < kPipe; ++j) {
           const int i = (rbase + j) * W + c;
-          va[j] = __ldg(vs + i);
-          vb[j] = __ldg(vs + N + i);
+          va[j] = ldg_stream(vs + i, pol);
+          vb[j] = ldg_stream(vs + N + i, pol);
           asm volatile("prefetch.global.L1 [%0];" ::"l"(us + i));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(us + N + i));
         }
@@ -510,8 +534,8 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           for (int j = 0; j < kPipe; ++j) {
             const int kn = min(k0 + kPipe + j, NB - 1);          // last group: harmless re-read of its own rows
             const int i = (rbase + kn) * W + c;
-            na[j] = __ldg(vs + i);
-            nb[j] = __ldg(vs + N + i);
+            na[j] = ldg_stream(vs + i, pol);
+            nb[j] = ldg_stream(vs + N + i, pol);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(us + i));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(us + N + i));
           }
@@ -522,8 +546,8 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
             const float v0 = va[j], v1 = vb[j];
             const Taps t = make_taps<BG>((float)r + mdt * v0, (float)c + mdt * v1, H, W);
             float a0, a1, b0, b1;
-            tap_grad<BG>(t, __ldg(us + t.o00), __ldg(us + t.o10), __ldg(us + t.o01), __ldg(us + t.o11), a0, a1);
-            tap_grad<BG>(t, __ldg(us + N + t.o00), __ldg(us + N + t.o10), __ldg(us + N + t.o01), __ldg(us + N + t.o11), b0, b1);
+            tap_grad<BG>(t, ldg_stream(us + t.o00, pol), ldg_stream(us + t.o10, pol), ldg_stream(us + t.o01, pol), ldg_stream(us + t.o11, pol), a0, a1);
+            tap_grad<BG>(t, ldg_stream(us + N + t.o00, pol), ldg_stream(us + N + t.o10, pol), ldg_stream(us + N + t.o01, pol), ldg_stream(us + N + t.o11, pol), b0, b1);
             z[r * LD + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
             splat2_agg<BG>(Gnext, N, t, g0, g1, cy, lane);
           }
@@ -535,11 +559,11 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
         for (int k = 0; k < NB; ++k) {
           const int r = rbase + k, i = r * W + c;
           const float g0 = __ldcg(Gcur + i), g1 = __ldcg(Gcur + N + i);
-          const float v0 = __ldg(vs + i), v1 = __ldg(vs + N + i);
+          const float v0 = ldg_stream(vs + i, pol), v1 = ldg_stream(vs + N + i, pol);
           const Taps t = make_taps<BG>((float)r + mdt * v0, (float)c + mdt * v1, H, W);
           float a0, a1, b0, b1;
-          tap_grad<BG>(t, __ldg(us + t.o00), __ldg(us + t.o10), __ldg(us + t.o01), __ldg(us + t.o11), a0, a1);
-          tap_grad<BG>(t, __ldg(us + N + t.o00), __ldg(us + N + t.o10), __ldg(us + N + t.o01), __ldg(us + N + t.o11), b0, b1);
+          tap_grad<BG>(t, ldg_stream(us + t.o00, pol), ldg_stream(us + t.o10, pol), ldg_stream(us + t.o01, pol), ldg_stream(us + t.o11, pol), a0, a1);
+          tap_grad<BG>(t, ldg_stream(us + N + t.o00, pol), ldg_stream(us + N + t.o10, pol), ldg_stream(us + N + t.o01, pol), ldg_stream(us + N + t.o11, pol), b0, b1);
           z[r * LD + c] = make_float2(mdt * (g0 * a0 + g1 * b0 + g0), mdt * (g0 * a1 + g1 * b1 + g1));
           splat2_agg<BG>(Gnext, N, t, g0, g1, cy, lane);
         }
@@ -580,12 +604,12 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
           const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
           const float sr = diff_scale(r, H);
-          const float d00 = sr * (__ldg(us + odn) - __ldg(us + oup)), d10 = sr * (__ldg(us + N + odn) - __ldg(us + N + oup));
-          const float d01 = sc * (__ldg(us + ort) - __ldg(us + olf)), d11 = sc * (__ldg(us + N + ort) - __ldg(us + N + olf));
+          const float d00 = sr * (ldg_stream(us + odn, pol) - ldg_stream(us + oup, pol)), d10 = sr * (ldg_stream(us + N + odn, pol) - ldg_stream(us + N + oup, pol));
+          const float d01 = sc * (ldg_stream(us + ort, pol) - ldg_stream(us + olf, pol)), d11 = sc * (ldg_stream(us + N + ort, pol) - ldg_stream(us + N + olf, pol));
           const float2 g = z[r * LD + c];
           const float gw0 = g.x + (d00 * g.x + d01 * g.y);
           const float gw1 = g.y + (d10 * g.x + d11 * g.y);
-          const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
+          const Taps t = make_taps<BG>((float)r + ldg_stream(us + i, pol), (float)c + ldg_stream(us + N + i, pol), H, W);
           splat2_agg<BG>(A, N, t, gw0, gw1, cy, lane);
           float w0, w1, o0, o1;
           {
