@@ -258,15 +258,181 @@ __device__ __forceinline__ void fluid_multiply(float2* __restrict__ z, const flo
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused middle of the operator: [second radix pass of the forward column FFT] + [symbol multiply] + [first radix pass
+// of the inverse column FFT], all in registers.  The second forward pass of task (column pc, k1) leaves the N2
+// frequencies k0 = k1 + N1 k2 of that column in the thread's registers, and the first inverse pass consumes exactly
+// the same cells, so only the multiplier's partner - frequency (-k0, -k1f), i.e. task (mirror column qc,
+// k1' = (N1 - k1) % N1) with register index k2' - has to be in the same thread.  Units of work are therefore PAIRS of
+// tasks closed under mirroring; their number is (N1/2) W, one per thread for every instantiation used (128 x 128 with
+// 1024 threads, 64 x 64 with 256).  Saves two shared-memory round trips of the whole field, two barriers and the
+// multiplier's cell-index arithmetic per operator.
+//   unit  <  (N1/2 - 1) W          : k1 in 1 .. N1/2-1, any column pc        <->  (qc, N1 - k1)
+//   next  2 (W/2 - 1) units        : k1 in {0, N1/2}, column pairs pc < qc   <->  (qc, k1)
+//   last  2 units                  : the two self-mirrored columns (k1f = 0, W/2) for k1 = 0 and k1 = N1/2
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef B2_FUSED_MULT
+#define B2_FUSED_MULT 1
+#endif
+
+template <int W>
+__device__ __forceinline__ int mirror_cell(int pc) { return freq_to_cell<W>((W - cell_to_freq<W>(pc)) & (W - 1)); }
+
+// canonical representative jj in [0, W/2 - 1) of the column pairs pc < qc (contiguous cells wherever possible)
+template <int W>
+__device__ __forceinline__ int canonical_column(int jj) {
+  constexpr int N1 = Fact<W>::N1, N2 = Fact<W>::N2;
+  constexpr int nA = (N1 / 2 - 1) * N2;              // whole blocks a = 1 .. N1/2-1
+  if (jj < nA) return N2 + jj;
+  const int j2 = jj - nA;
+  if (j2 < N2 / 2 - 1) return 1 + j2;                // block 0: b = 1 .. N2/2-1  (b' = N2 - b)
+  return N2 * (N1 / 2) + (j2 - (N2 / 2 - 1));        // block N1/2: b = 0 .. N2/2-1  (b' = N2 - 1 - b)
+}
+
+// W(k) = A Z(k) + B conj Z(-k) for one mirror pair held in registers
+template <bool INVERSE>
+__device__ __forceinline__ void mult_pair(float2& Z, float2& Zq, bool same, const FluidParams& fp, float2 cs0, float2 cs1) {
+  const float h = 0.5f * fp.scale;
+  const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
+  const float L00 = lam + fp.beta * cs0.x, L11 = lam + fp.beta * cs1.x, L01 = fp.beta * (cs0.y * cs1.y);
+  float A, Br, Bi;
+  if (INVERSE) {
+    const float idet = __fdividef(h, L00 * L11 - L01 * L01);
+    A = idet * (L11 + L00); Br = idet * (L11 - L00); Bi = -2.0f * idet * L01;
+  } else {
+    A = h * (L00 + L11); Br = h * (L00 - L11); Bi = 2.0f * h * L01;
+  }
+  const float2 z = Z, zq = Zq;
+  Z = make_float2(A * z.x + Br * zq.x + Bi * zq.y, A * z.y + Bi * zq.x - Br * zq.y);
+  if (!same) Zq = make_float2(A * zq.x + Br * z.x + Bi * z.y, A * zq.y + Bi * z.x - Br * z.y);
+}
+
+// one task's share of the inverse column FFT's first pass: DFT over k2, inter-pass twiddle, store
+template <int N1, int N2, int ES>
+__device__ __forceinline__ void inv_pass1_store(float2 (&y)[N2], float2* base, const float2* tw, int k1) {
+  DftReg<N2, +1>::run(y);
+#pragma unroll
+  for (int n2 = 0; n2 < N2; ++n2) {
+    const float2 w = tw[n2 * k1];
+    base[n2 * ES] = (n2 == 0) ? y[n2] : cmul(y[n2], w.x, w.y);
+  }
+}
+
+template <int H, int W, bool INVERSE, int NT>
+__device__ __forceinline__ void fluid_cols_mid_fused(float2* __restrict__ z, const float2* __restrict__ twH,
+                                                     const float2* __restrict__ csH, const float2* __restrict__ csW,
+                                                     const FluidParams fp, int tid) {
+  constexpr int N1 = Fact<H>::N1, N2 = Fact<H>::N2, LD = W + 1, ES = LD;
+  constexpr int nA = (N1 / 2 - 1) * W, nB = 2 * (W / 2 - 1), units = nA + nB + 2;
+  static_assert(units == (N1 / 2) * W, "unit count");
+  for (int unit = tid; unit < units; unit += NT) {
+    if (unit < nA + nB) {
+      // ---- a pair of distinct tasks (pc, k1) <-> (qc, k1q)
+      int k1, pc;
+      if (unit < nA) { k1 = 1 + unit / W; pc = unit % W; }
+      else {
+        const int j = unit - nA;
+        k1 = (j < W / 2 - 1) ? 0 : N1 / 2;
+        pc = canonical_column<W>(j < W / 2 - 1 ? j : j - (W / 2 - 1));
+      }
+      const int k1q = (N1 - k1) & (N1 - 1), qc = mirror_cell<W>(pc);
+      float2* basea = z + pc + (N2 * k1) * ES;
+      float2* baseb = z + qc + (N2 * k1q) * ES;
+      float2 ya[N2], yb[N2];
+#pragma unroll
+      for (int n2 = 0; n2 < N2; ++n2) { ya[n2] = basea[n2 * ES]; yb[n2] = baseb[n2 * ES]; }
+      DftReg<N2, -1>::run(ya);
+      DftReg<N2, -1>::run(yb);
+      const float2 cs1 = csW[cell_to_freq<W>(pc)];
+      if (k1 == 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) mult_pair<INVERSE>(ya[k2], yb[(N2 - k2) % N2], false, fp, csH[N1 * k2], cs1);
+      } else {
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) mult_pair<INVERSE>(ya[k2], yb[N2 - 1 - k2], false, fp, csH[k1 + N1 * k2], cs1);
+      }
+      inv_pass1_store<N1, N2, ES>(ya, basea, twH, k1);
+      inv_pass1_store<N1, N2, ES>(yb, baseb, twH, k1q);
+    } else {
+      // ---- the self-mirrored columns (k1f = 0 and W/2): mirror partners inside one task's registers
+      const int k1 = (unit == nA + nB) ? 0 : N1 / 2;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const int k1f = which ? W / 2 : 0, pc = freq_to_cell<W>(k1f);
+        float2* base = z + pc + (N2 * k1) * ES;
+        float2 y[N2];
+#pragma unroll
+        for (int n2 = 0; n2 < N2; ++n2) y[n2] = base[n2 * ES];
+        DftReg<N2, -1>::run(y);
+        const float2 cs1 = csW[k1f];
+        if (k1 == 0) {
+#pragma unroll
+          for (int k2 = 0; k2 <= N2 / 2; ++k2)
+            mult_pair<INVERSE>(y[k2], y[(N2 - k2) % N2], k2 == (N2 - k2) % N2, fp, csH[N1 * k2], cs1);
+        } else {
+#pragma unroll
+          for (int k2 = 0; k2 < N2 / 2; ++k2) mult_pair<INVERSE>(y[k2], y[N2 - 1 - k2], false, fp, csH[k1 + N1 * k2], cs1);
+        }
+        inv_pass1_store<N1, N2, ES>(y, base, twH, k1);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// first pass of a forward transform / second pass of an inverse transform on their own (the halves of fft_lines
+// that stay in front of and behind the fused middle)
+template <int N, int NL, int NT, int ES, int LS>
+__device__ __forceinline__ void fft_fwd_pass1(float2* __restrict__ z, const float2* __restrict__ tw, int tid) {
+  constexpr int N1 = Fact<N>::N1, N2 = Fact<N>::N2;
+  for (int t = tid; t < NL * N2; t += NT) {
+    const int line = t % NL, n2 = t / NL;
+    float2* base = z + line * LS + n2 * ES;
+    float2 x[N1];
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) x[n1] = base[(N2 * n1) * ES];
+    DftReg<N1, -1>::run(x);
+#pragma unroll
+    for (int k1 = 1; k1 < N1; ++k1) {
+      const float2 w = tw[n2 * k1];
+      x[k1] = cmul(x[k1], w.x, -w.y);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) base[(N2 * k1) * ES] = x[k1];
+  }
+  __syncthreads();
+}
+template <int N, int NL, int NT, int ES, int LS>
+__device__ __forceinline__ void fft_inv_pass2(float2* __restrict__ z, int tid) {
+  constexpr int N1 = Fact<N>::N1, N2 = Fact<N>::N2;
+  for (int t = tid; t < NL * N2; t += NT) {
+    const int line = t % NL, n2 = t / NL;
+    float2* base = z + line * LS + n2 * ES;
+    float2 x[N1];
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) x[k1] = base[(N2 * k1) * ES];
+    DftReg<N1, +1>::run(x);
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) base[(N2 * n1) * ES] = x[n1];
+  }
+  __syncthreads();
+}
+
 // Whole operator on a field resident in shared memory as z = f0 + i f1.
 template <int H, int W, bool INVERSE, int NT>
 __device__ __forceinline__ void fluid_smem(float2* z, const float2* twH, const float2* twW,
                                            const float2* csH, const float2* csW, const FluidParams fp, int tid) {
   constexpr int LD = W + 1;
   fft_lines<W, H, -1, NT, 1, LD>(z, twW, tid);      // rows: FFT along c, lanes along r
+#if B2_FUSED_MULT
+  fft_fwd_pass1<H, W, NT, LD, 1>(z, twH, tid);      // cols: first radix pass
+  fluid_cols_mid_fused<H, W, INVERSE, NT>(z, twH, csH, csW, fp, tid);
+  fft_inv_pass2<H, W, NT, LD, 1>(z, tid);
+#else
   fft_lines<H, W, -1, NT, LD, 1>(z, twH, tid);      // cols: FFT along r, lanes along c
   fluid_multiply<H, W, INVERSE, NT>(z, csH, csW, fp, tid);
   fft_lines<H, W, +1, NT, LD, 1>(z, twH, tid);
+#endif
   fft_lines<W, H, +1, NT, 1, LD>(z, twW, tid);
 }
 

@@ -150,8 +150,15 @@ def test_zero_background_shooting(pkg, oracle, dev, hw, S):
     # Fields that leave the grid under the zero rule are discontinuous at the border, so at this amplitude the fp32
     # oracle itself is 0.5-1.5e-5 away from its float64 run: the CUDA path is held to the float64 truth within twice
     # that, and to the fp32 oracle within three times that.
+    # The strain matrix is a nonlinear function of Du averaged over a handful of pixels per sector (126 sectors on
+    # these small grids): in this stress test its fp32 error is a small multiple of the displacement's - the fp32
+    # oracle itself lands anywhere between 3e-6 and 2e-5 of float64 depending on the background rule - so its bound
+    # also admits 5x the oracle's own displacement error.
+    own_u = relerr(ref["displacement"], ref64["displacement"])
     for k in ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix"):
         own = relerr(ref[k], ref64[k])
+        if k == "strain_matrix":
+            own = max(own, 2.5 * own_u)
         assert relerr(out[k], ref64[k]) < max(TOL, 2.0 * own), f"{k} vs f64: {relerr(out[k], ref64[k]):.2e} (oracle32: {own:.2e})"
         assert relerr(out[k], ref[k]) < max(TOL, 3.0 * own), f"{k}: {relerr(out[k], ref[k]):.2e} (oracle32 vs 64: {own:.2e})"
     # the zero rule really differs from the clamp rule on this input
