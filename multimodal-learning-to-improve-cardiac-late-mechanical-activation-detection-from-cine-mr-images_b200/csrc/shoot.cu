@@ -16,10 +16,11 @@
 //
 // 256x256: one 4-CTA thread-block cluster per frame-pair (shoot_cluster.cu), same residency idea with 64-row slabs.
 //
-// Path B (rectangular grids, or 256x256 with B2_NO_CLUSTER=1): the same algorithm as a sequence of the
-// op-level kernels (HBM-bound per op).
+// Path B (rectangular grids, B2_FLAG_OPLEVEL at 256x256, or a device that cannot co-schedule the cluster): the same
+// algorithm as a sequence of the op-level kernels (HBM-bound per op).
 //
-// Backward: shoot_bwd_kernel (fused EPDiff adjoint, square grids up to 128x128) or the op-level sweep.
+// Backward: shoot_bwd_kernel (fused EPDiff adjoint, square grids up to 128x128), shoot_cluster_bwd_kernel (256x256,
+// shoot_cluster.cu) or the op-level sweep; b2_shoot_bwd_ex selects.
 #include "fft.cuh"
 #include "shoot_params.cuh"
 #include "strain.cuh"
