@@ -51,6 +51,7 @@ int epdiff_step_big(const float* u, const float* m0, float* unext, float* vout, 
                     int64_t W, float alpha, float beta, float gamma, float dt, int bg, cudaStream_t st);
 
 constexpr int kFusedMaxSectors = 256;
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 #ifndef B2_FAST_GATHER
 #define B2_FAST_GATHER 0
 #endif
@@ -62,10 +63,28 @@ constexpr int kComposeUnroll = B2_COMPOSE_UNROLL;
 
 struct ShootParams {
   b2_shoot_args a;
-  float* scratch;     // per-CTA: [u ping-pong | m0] fields
+  float* scratch;     // per-CTA: [u ping-pong | m0] fields; balanced schedule: + per-CTA hand-off [u_h | m0] + flags
   int64_t P;
   int64_t field;      // 2*H*W floats
+  int balanced;       // != 0: contiguous, equal-cost ranges of the pair timeline per CTA (split_schedule)
 };
+
+// ---- dynamic schedule of the persistent grid (removes the partial last wave) ----------------------------------
+// With one CTA per pair at a time and P not a multiple of the grid, the last wave runs on a fraction of the SMs
+// (configs[1]: 1536 pairs on 148 CTAs = 10.38 waves, 5.6 % of the kernel idle), and SMs do not all run at the same
+// speed.  A geodesic cannot be split in space at 128x128, but it can be HANDED OVER between steps: its whole state at
+// a step boundary is (u_s, m0) in global memory.  Work is therefore drawn from ONE atomic ticket counter:
+//   tickets [0, P - K)            whole pairs (K = grid size: the last K pairs are the "tail"),
+//   tickets P - K + c K + i       chunk c (kChunkSteps EPDiff steps) of tail pair i; chunk 0 includes the prologue,
+//                                 the last chunk the epilogue.
+// Chunks of one pair are K tickets apart, so by the time chunk c of a pair is drawn its chunk c-1 was drawn K tickets
+// earlier (normally finished; a flag per (pair, chunk) makes it a guarantee).  The CTA that holds an earlier ticket is
+// running, so waits cannot deadlock.  The kernel ends within one chunk of perfect balance instead of one pair, and
+// fast SMs simply draw more tickets.  Same arithmetic per pair whoever executes it: results are bit-identical.
+constexpr int kChunkSteps = 2;     // >= 2: a chunk's first step reads the hand-over buffer, its last step rewrites it
+#ifndef B2_BALANCED
+#define B2_BALANCED 1              // 0: static schedule (CTA j takes pairs j, j + G, ...)
+#endif
 
 template <int H, int W>
 struct ShootSmem {
@@ -107,12 +126,57 @@ shoot_fwd_kernel(const ShootParams prm) {
   float* scr_m = scr_u + prm.field;
   __syncthreads();
 
-  for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
+  // work items are drawn from the ticket counter (see above); without the dynamic schedule (few pairs) CTA j takes
+  // pairs j, j + G, ...
+  const int64_t G = gridDim.x, cta = blockIdx.x;
+  const int64_t K = prm.balanced ? G : 0;                       // tail pairs, handed over between chunks of steps
+  const int n_chunks = prm.balanced ? S / kChunkSteps : 1;      // the last chunk takes the remainder of an odd S
+  float* hand = prm.scratch + (size_t)G * 2 * prm.field;        // hand-over [u_s | m0] of tail pair i
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(hand + (size_t)G * 2 * prm.field);   // zeroed per launch
+  int* flags = reinterpret_cast<int*>(ticket + 2);              // flags[i * n_chunks + c] = chunk c of tail pair i done
+  __shared__ long long item_s;
+
+  for (int64_t it = 0;; ++it) {
+    int64_t p;
+    int s0 = 0, s1 = S;
+    float *hand_out = nullptr, *hand_in = nullptr;     // this item ends / starts at a hand-over
+    int* flag_out = nullptr;
+    if (!prm.balanced) {
+      p = cta + it * G;
+      if (p >= P) break;
+    } else {
+      if (tid == 0) item_s = (long long)atomicAdd(ticket, 1ull);
+      __syncthreads();
+      const int64_t tk = item_s;
+      __syncthreads();                                   // everyone has read the ticket before the next draw
+      if (tk < P - K) p = tk;
+      else {
+        const int64_t q = tk - (P - K);
+        if (q >= K * n_chunks) break;
+        const int ch = (int)(q / K);
+        const int64_t i = q % K;
+        p = P - K + i;
+        s0 = ch * kChunkSteps;
+        s1 = (ch == n_chunks - 1) ? S : s0 + kChunkSteps;
+        float* hb = hand + (size_t)i * 2 * prm.field;
+        if (s0 > 0) {
+          hand_in = hb;
+          if (tid == 0) {                                // the chunk before this one (drawn K tickets ago) is done
+            while (*reinterpret_cast<volatile int*>(flags + i * n_chunks + ch - 1) == 0) __nanosleep(200);
+            __threadfence();
+          }
+          __syncthreads();
+        }
+        if (s1 < S) { hand_out = hb; flag_out = flags + i * n_chunks + ch; }
+      }
+    }
     const int64_t b = p / a.T1;
     const int t = (int)(p % a.T1);
     const float* m0g;
     float* uout = a.u + (size_t)p * prm.field;
+    const float* ucur = nullptr;   // u_s in global memory (nullptr == identically zero)
 
+    if (s0 == 0) {
     // ---- m0 = flat(v0)   (or m0 given directly: lagomorph.expmap(metric, m0))
     {
       const float* f0 = a.v0 + (size_t)p * prm.field;
@@ -126,7 +190,8 @@ shoot_fwd_kernel(const ShootParams prm) {
     if (a.v0_is_momentum) {
       m0g = a.v0 + (size_t)p * prm.field;
     } else {
-      float* m0w = a.m0 ? a.m0 + (size_t)p * prm.field : scr_m;
+      // a pair that will be finished by another CTA keeps its momentum where that CTA finds it
+      float* m0w = a.m0 ? a.m0 + (size_t)p * prm.field : (hand_out ? hand_out + prm.field : scr_m);
       fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
 #pragma unroll 4
       for (int k = 0; k < NB; ++k) {
@@ -138,9 +203,20 @@ shoot_fwd_kernel(const ShootParams prm) {
       m0g = m0w;
       __syncthreads();   // every thread has read z before the next transform overwrites it
     }
+    } else {
+      // ---- take over a geodesic at step s0 (its earlier chunks are done, see the wait above): reload u_{s0} into
+      // the shared-memory field; m0 and u_{s0} are where the previous chunk left them
+      m0g = a.v0_is_momentum ? a.v0 + (size_t)p * prm.field : (a.m0 ? a.m0 + (size_t)p * prm.field : hand_in + prm.field);
+      ucur = a.traj ? a.traj + ((size_t)(s0 * 2) * P + p) * prm.field : hand_in;
+#pragma unroll 4
+      for (int k = 0; k < NB; ++k) {
+        const int r = k * RB + br;
+        z[r * LD + c] = make_float2(__ldcg(ucur + r * W + c), __ldcg(ucur + N + r * W + c));
+      }
+      __syncthreads();
+    }
 
-    const float* ucur = nullptr;   // u_s in global memory (nullptr == identically zero)
-    for (int s = 0; s < S; ++s) {
+    for (int s = s0; s < s1; ++s) {
       // ---- m = Ad*_{u_s} m0 -> z.  z holds u_s (float2 per pixel, written by the previous compose):
       // the (I + Du)^T stencil reads shared memory; only the 4-tap gather of m0 goes to L1/L2.
       // Band k is overwritten with m only after every thread has read it (one barrier per band); the
@@ -184,6 +260,7 @@ shoot_fwd_kernel(const ShootParams prm) {
       // in place of v, into z (stencil of the next Ad*); trajectory / velocity outputs
       float* unext;
       if (a.traj) unext = (s + 1 < S) ? a.traj + ((size_t)((s + 1) * 2 + 0) * P + p) * prm.field : uout;
+      else if (hand_out && s + 1 == s1) unext = hand_out;        // last step of a head piece: u_h for the finisher
       else unext = (((S - (s + 1)) & 1) == 0) ? uout : scr_u;
       float* vtraj = a.traj ? a.traj + ((size_t)(s * 2 + 1) * P + p) * prm.field : nullptr;
       if (s == 0) {
@@ -227,6 +304,14 @@ shoot_fwd_kernel(const ShootParams prm) {
       }
       ucur = unext;
       __syncthreads();   // u_{s+1} visible to the whole CTA (global and shared copies)
+    }
+    if (hand_out) {
+      // chunk done: publish (u_s1, m0) to whoever draws the next chunk of this pair (release: barrier above, fence)
+      if (tid == 0) {
+        __threadfence();
+        atomicExch(flag_out, 1);
+      }
+      continue;
     }
 
     // ---- deformed_source = interp(src, u^S)
@@ -759,7 +844,6 @@ static int axpby(float* y, const float* x, float a, float b, size_t n, cudaStrea
   return B2_OK;
 }
 
-static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace b2
 
@@ -772,7 +856,12 @@ extern "C" int64_t b2_shoot_workspace_bytes(int64_t B, int64_t T1, int64_t H, in
 extern "C" int64_t b2_shoot_workspace_bytes_flags(int64_t B, int64_t T1, int64_t H, int64_t W, int num_steps, int flags) {
   if (B <= 0 || T1 <= 0 || H <= 0 || W <= 0 || num_steps <= 0) return 0;
   const int64_t P = B * T1, field = 2 * H * W;
-  if (fused_size(H, W, flags)) return (int64_t)align256(sizeof(float) * (size_t)fused_grid(P, H) * 2 * field);
+  // per-CTA scratch [u | m0], hand-over [u_s | m0] of the tail pairs of the dynamic schedule, ticket counter + one
+  // flag per (tail pair, chunk of steps)
+  if (fused_size(H, W, flags)) {
+    const size_t g = (size_t)fused_grid(P, H);
+    return (int64_t)(align256(sizeof(float) * g * 4 * field) + align256(16 + sizeof(int) * g * (size_t)(num_steps / kChunkSteps + 1)));
+  }
   if (cluster_size(H, W, P, flags)) return (int64_t)align256((size_t)cluster_workspace_bytes(P));
   // path B: m0 (if not given) + u scratch + m/v buffer + FFT scratch
   return (int64_t)(3 * align256(sizeof(float) * (size_t)P * field) + align256((size_t)b2_fluid_workspace_bytes(P, H, W)));
@@ -804,6 +893,12 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
     prm.P = P;
     prm.field = field;
     const int64_t grid = fused_grid(P, H);
+    // dynamic schedule (ticket counter + hand-over of the tail pairs): worth it once every CTA has at least two
+    // pairs; its counter and flags sit behind the scratch and are cleared on the stream in front of the kernel
+    prm.balanced = (B2_BALANCED && P >= 2 * grid && a.num_steps >= 2 * kChunkSteps) ? 1 : 0;
+    if (prm.balanced)
+      B2_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(workspace) + align256(sizeof(float) * (size_t)grid * 4 * field),
+                              0, 16 + sizeof(int) * (size_t)grid * (size_t)(a.num_steps / kChunkSteps + 1), st));
     switch ((int)H) {
       case 16: return launch_fused<16, 16, 128>(prm, grid, st);
       case 32: return launch_fused<32, 32, 256>(prm, grid, st);
