@@ -318,6 +318,11 @@ int b2_unpack_u8(const uint8_t* in, float* out, int64_t n, void* stream);
 
 /* Device properties the host side needs for grid sizing / reporting. */
 int b2_device_sm_count(int device);
+/* 256x256 shooting: how many 4-CTA clusters of the fused kernel are co-resident on the current device (0 = clusters
+ * unavailable) and how many SMs they leave without a CTA (a 4-SM cluster must sit inside one GPC, so GPCs whose SM
+ * count is not a multiple of 4 strand SMs: 33 clusters / 16 idle SMs on a 148-SM B200).  The host side uses the idle
+ * SMs for op-level work on a second stream (shooting.py, `idle_sm_split`). */
+int b2_shoot_cluster_occupancy(int* clusters, int* idle_sms);
 
 #ifdef __cplusplus
 }

@@ -130,6 +130,14 @@ __device__ __forceinline__ void tap_grad(const Taps& t, float v00, float v10, fl
 // issues ~1 RED per plane instead of 4 (index compares decide: any mismatch - floor crossing, image edge, warp
 // edge - falls back to direct atomics, so the sum is always complete).  All 32 lanes must call converged.
 // ---------------------------------------------------------------------------
+// Fire-and-forget float reduction into GLOBAL memory.  atomicAdd() with an unused result normally becomes RED too, but
+// ptxas keeps the returning form (ATOMG: the issuing warp waits for the old value) in every kernel that also contains
+// a __threadfence() - the hand-over of the dynamic schedule - which cost the adjoint kernel 12 % before this was
+// spelled out.
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+
 struct SplatCarry {
   int idx;       // flat target index of the carried bottom-left contribution, -1 = empty
   float a, b;    // plane 0 / plane 1 values
@@ -137,8 +145,8 @@ struct SplatCarry {
 
 __device__ __forceinline__ void splat_flush(float* __restrict__ G, int plane, SplatCarry& cy) {
   if (cy.idx >= 0) {
-    atomicAdd(G + cy.idx, cy.a);
-    atomicAdd(G + plane + cy.idx, cy.b);
+    red_add(G + cy.idx, cy.a);
+    red_add(G + plane + cy.idx, cy.b);
   }
   cy.idx = -1;
 }
@@ -161,13 +169,13 @@ __device__ __forceinline__ void splat2_agg(float* __restrict__ G, int plane, con
   const bool given = (__shfl_down_sync(full, (int)take, 1) != 0) && lane < 31;
   if (take) { aT += naT; bT += nbT; aB += naB; bB += nbB; }
   if (!given) {
-    atomicAdd(G + t.o01, aTr); atomicAdd(G + plane + t.o01, bTr);
-    atomicAdd(G + t.o11, aBr); atomicAdd(G + plane + t.o11, bBr);
+    red_add(G + t.o01, aTr); red_add(G + plane + t.o01, bTr);
+    red_add(G + t.o11, aBr); red_add(G + plane + t.o11, bBr);
   }
   if (cy.idx == t.o00) { aT += cy.a; bT += cy.b; }
   else splat_flush(G, plane, cy);
-  atomicAdd(G + t.o00, aT);
-  atomicAdd(G + plane + t.o00, bT);
+  red_add(G + t.o00, aT);
+  red_add(G + plane + t.o00, bT);
   cy.idx = t.o10; cy.a = aB; cy.b = bB;
 }
 

@@ -81,6 +81,10 @@ struct ShootParams {
 // earlier (normally finished; a flag per (pair, chunk) makes it a guarantee).  The CTA that holds an earlier ticket is
 // running, so waits cannot deadlock.  The kernel ends within one chunk of perfect balance instead of one pair, and
 // fast SMs simply draw more tickets.  Same arithmetic per pair whoever executes it: results are bit-identical.
+#ifndef B2_BALANCED_BWD
+#define B2_BALANCED_BWD 1
+#endif
+constexpr int kBwdMaxChunks = 64;
 constexpr int kChunkSteps = 2;     // >= 2: a chunk's first step reads the hand-over buffer, its last step rewrites it
 #ifndef B2_BALANCED
 #define B2_BALANCED 1              // 0: static schedule (CTA j takes pairs j, j + G, ...)
@@ -530,18 +534,64 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
   const float c0c = (c == W - 1 ? 1.f : 0.f) - (c == 0 ? 1.f : 0.f);
   FS::init_luts(twH, twW, csH, csW, tid, NT);
   const unsigned long long pol = make_evict_first_policy();
-  float* Ga = prm.scratch + (size_t)blockIdx.x * 3 * prm.field;
-  float* Gb = Ga + prm.field;
-  float* A = Gb + prm.field;
   const BwdSeed& sd = prm.seed;
   int32_t* tab_s = reinterpret_cast<int32_t*>(smem_raw + BwdSmem<H, W>::seed_off);      // seeds: sector table
   float* gk_s = reinterpret_cast<float*>(tab_s + 2 * kFusedMaxSectors);                   //        + per-sector weights
+  // Work items come from the same kind of ticket counter as in shoot_fwd_kernel: whole pairs first, then the last
+  // K = grid-size pairs in chunks of `chunk_steps` adjoint steps, so that no CTA is left with a whole pair while the
+  // others are done.  The state of the reverse sweep at a step boundary is (dL/du_s, dL/dm0), all of it in the scratch
+  // and written through L2 (stcg / RED): a tail pair uses three scratch fields of its own (slots G .. 2G-1, behind the
+  // per-CTA ones), so a chunk continues where the previous one stopped - whoever ran it.  Thread 0 draws and decodes
+  // the item; the descriptor lives in shared memory and is read where it is needed (the kernel sits at its register
+  // limit: a descriptor in registers spilled inside the hot loops and cost more than the schedule gained).
+  __shared__ int item_sh[6];      // pair, first step, last step, scratch slot, flag to publish (-1: none), round
+  if (tid == 0) item_sh[5] = 0;
   __syncthreads();
 
-  for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
+  for (;;) {
+    if (tid == 0) {
+      const int64_t G = gridDim.x;
+      int64_t pp = -1;
+      int s_hi = S - 1, s_lo = 0, pub = -1;
+      int64_t slot = blockIdx.x;
+      if (!prm.ticket) {
+        const int64_t q = blockIdx.x + (int64_t)item_sh[5] * G;
+        if (q < P) pp = q;
+        item_sh[5] += 1;
+      } else {
+        const int cs = prm.chunk_steps, n_chunks = S / cs;       // the last chunk takes the remainder
+        const int64_t tk = (int64_t)atomicAdd(prm.ticket, 1ull);
+        if (tk < P - G) pp = tk;
+        else if (tk - (P - G) < G * n_chunks) {
+          const int64_t q = tk - (P - G);
+          const int ch = (int)(q / G);
+          const int64_t i = q % G;
+          pp = P - G + i;
+          slot = G + i;
+          s_hi = S - 1 - ch * cs;
+          s_lo = (ch == n_chunks - 1) ? 0 : s_hi - cs + 1;
+          if (ch > 0) {                                  // the chunk before this one (drawn G tickets ago)
+            while (*reinterpret_cast<volatile int*>(prm.flags + i * n_chunks + ch - 1) == 0) __nanosleep(200);
+            __threadfence();                             // acquire
+          }
+          if (s_lo > 0) pub = (int)(i * n_chunks + ch);
+        }
+      }
+      item_sh[0] = (int)pp; item_sh[1] = s_hi; item_sh[2] = s_lo; item_sh[3] = (int)slot; item_sh[4] = pub;
+    }
+    __syncthreads();
+    if (item_sh[0] < 0) break;
+    const int64_t p = item_sh[0];
+    const int s_hi = item_sh[1];
+    float* Ga = prm.scratch + (size_t)item_sh[3] * 3 * prm.field;
+    float* Gb = Ga + prm.field;
+    float* A = Gb + prm.field;
     const float* m0p = prm.m0 + (size_t)p * prm.field;
-    float* Gcur = Ga;
-    float* Gnext = Gb;
+    // every adjoint step with s > 0 swaps the two dL/du buffers: after the steps S-1 .. s_hi+1 the current one is
+    const bool swapped = ((S - 1 - s_hi) & 1) != 0;
+    float* Gcur = swapped ? Gb : Ga;
+    float* Gnext = swapped ? Ga : Gb;
+    if (s_hi == S - 1) {                              // first chunk of the pair: seed dL/du^S and dL/dm0
     for (int k = 0; k < NB; ++k) {
       const int i = (rbase + k) * W + c;
       Gcur[i] = prm.gu ? __ldg(prm.gu + (size_t)p * prm.field + i) : 0.f;
@@ -579,14 +629,15 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           const float g = g2 * (tap_sample<BG>(tp, v00, v10, v01, v11) - __ldg(tarp + i));
           float a0, a1;
           tap_grad<BG>(tp, v00, v10, v01, v11, a0, a1);
-          atomicAdd(Gcur + i, g * a0);       // RED: the strain adjoint of neighbouring pixels may target this pixel too
-          atomicAdd(Gcur + N + i, g * a1);
+          red_add(Gcur + i, g * a0);       // RED: the strain adjoint of neighbouring pixels may target this pixel too
+          red_add(Gcur + N + i, g * a1);
         }
       }
     }
+    }
     __syncthreads();
 
-    for (int s = S - 1; s >= 0; --s) {
+    for (int s = s_hi; s >= *reinterpret_cast<volatile int*>(item_sh + 2); --s) {
       const float* us = prm.traj + ((size_t)(2 * s) * P + p) * prm.field;
       const float* vs = prm.traj + ((size_t)(2 * s + 1) * P + p) * prm.field;
       if (s > 0) {
@@ -754,10 +805,18 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       }
       __syncthreads();
     }
+    if (item_sh[4] >= 0) {
+      // chunk done (the barrier closing its last step is behind us): publish (dL/du_s, dL/dm0) to whoever draws
+      // the next chunk of this pair
+      const int pub = item_sh[4];
+      __syncthreads();                                   // descriptor read by everyone before thread 0 redraws
+      if (tid == 0) {
+        __threadfence();
+        atomicExch(prm.flags + pub, 1);
+      }
+      continue;
+    }
     // ---- dL/dv0 = flat(dL/dm0)  (or dL/dm0 itself when the forward input was the momentum)
-    if (S >= 2 && p + gridDim.x < P)      // first trajectory entry the next pair of this CTA will read
-      prefetch_traj_l2<NT>(prm.traj + ((size_t)(2 * S - 2) * P + p + gridDim.x) * prm.field,
-                           prm.traj + ((size_t)(2 * S - 1) * P + p + gridDim.x) * prm.field, (int)prm.field, tid);
     if (!prm.v0_is_momentum) fluid_smem<H, W, false, NT>(z, twH, twW, csH, csW, fp, tid);
     float* out = prm.gv0 + (size_t)p * prm.field;
     // d<sharp(m0), m0>/dm0 = 2 vel and flat(2 vel) = 2 m0: the regularisation gradient needs no transform
@@ -808,9 +867,21 @@ static int64_t fused_bwd_grid(int64_t P, int64_t H) {
 }
 
 template <int H, int W, int NT>
-static int launch_fused_bwd(const ShootBwdParams& prm, int background, cudaStream_t st) {
+static int launch_fused_bwd(const ShootBwdParams& prm_in, int background, cudaStream_t st) {
   const size_t smem = BwdSmem<H, W>::bytes;
-  const int64_t grid = fused_bwd_grid(prm.P, H);
+  const int64_t grid = fused_bwd_grid(prm_in.P, H);
+  ShootBwdParams prm = prm_in;
+  // dynamic schedule: worth it once every CTA has at least two pairs; at most kBwdMaxChunks chunks per tail pair (the
+  // workspace query does not know the step count).  Ticket + flags sit behind the 2 x grid scratch slots.
+  int cs = kChunkSteps;
+  while (prm.num_steps / cs > kBwdMaxChunks) ++cs;
+  prm.ticket = nullptr; prm.flags = nullptr; prm.chunk_steps = cs;
+  if (B2_BALANCED_BWD && prm.P >= 2 * grid && prm.num_steps >= 2 * cs) {
+    unsigned char* tk = reinterpret_cast<unsigned char*>(prm.scratch) + align256(sizeof(float) * (size_t)grid * 6 * prm.field);
+    prm.ticket = reinterpret_cast<unsigned long long*>(tk);
+    prm.flags = reinterpret_cast<int*>(tk + 16);
+    B2_CUDA(cudaMemsetAsync(tk, 0, 16 + sizeof(int) * (size_t)grid * kBwdMaxChunks, st));
+  }
   if (background == B2_BG_CLAMP) {
     B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP><<<(unsigned)grid, NT, smem, st>>>(prm);
@@ -980,7 +1051,11 @@ extern "C" int64_t b2_shoot_bwd_workspace_bytes(int64_t P, int64_t H, int64_t W)
 // sized per path: resident CTAs (clusters) x 3 fields for the fused adjoints, 5 P fields + FFT scratch op-level
 extern "C" int64_t b2_shoot_bwd_workspace_bytes_flags(int64_t P, int64_t H, int64_t W, int flags) {
   if (P <= 0 || H <= 0 || W <= 0) return 0;
-  if (fused_size(H, W, flags)) return (int64_t)align256(sizeof(float) * (size_t)fused_bwd_grid(P, H) * 3 * 2 * H * W);
+  // per-CTA scratch (3 fields), the tail pairs' own scratch of the dynamic schedule (3 fields each), ticket + flags
+  if (fused_size(H, W, flags)) {
+    const size_t g = (size_t)fused_bwd_grid(P, H);
+    return (int64_t)(align256(sizeof(float) * g * 6 * 2 * H * W) + align256(16 + sizeof(int) * g * kBwdMaxChunks));
+  }
   if (cluster_bwd_size(H, W, P, flags)) return (int64_t)align256((size_t)cluster_bwd_workspace_bytes(P));
   const int64_t fw = b2_fluid_workspace_bytes(P, H, W);   // 0 for grids whose FFT runs in shared memory
   return (int64_t)(5 * align256(sizeof(float) * (size_t)P * 2 * H * W) + align256((size_t)fw));
@@ -1106,6 +1181,17 @@ extern "C" int b2_device_sm_count(int device) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   return sms;
+}
+
+extern "C" int b2_shoot_cluster_occupancy(int* clusters, int* idle_sms) {
+  if (!clusters || !idle_sms) return B2_E_NULL;
+  int dev = 0, sms = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n = cluster_grid_clusters((int64_t)1 << 20);
+  *clusters = n;
+  *idle_sms = n > 0 ? sms - 4 * n : 0;
+  return B2_OK;
 }
 
 extern "C" int b2_version(void) { return 100; }

@@ -38,6 +38,10 @@ struct ShootBwdParams {
   int num_steps, v0_is_momentum;
   float alpha, beta, gamma, T;
   BwdSeed seed;         // all-null = none
+  // dynamic ticket schedule of the single-CTA kernel (shoot.cu): null ticket = static round-robin over the pairs
+  unsigned long long* ticket;   // zeroed per launch
+  int* flags;                   // flags[i * n_chunks + c] = chunk c of tail pair i done (zeroed per launch)
+  int chunk_steps;              // adjoint steps per chunk of a tail pair
 };
 
 }  // namespace b2

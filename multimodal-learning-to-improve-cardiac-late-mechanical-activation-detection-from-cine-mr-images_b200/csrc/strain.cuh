@@ -106,13 +106,13 @@ __device__ __forceinline__ void strain_bwd_frame(const float* u0, const float* u
     const float g_e1 = -g_t0 * e.G01 + g_t1 * e.G00;
     const float g_n0 = 2.f * e.n0 * g_rad2 + g_e1;
     const float g_n1 = 2.f * e.n1 * g_rad2 - g_e0;
-    atomicAdd(d0 + x, g_n0);
-    atomicAdd(d1 + x, g_n1);
+    red_add(d0 + x, g_n0);
+    red_add(d1 + x, g_n1);
     // G00 = 1 + d0 u0, G10 = d0 u1 (row differences); G01 = d1 u0, G11 = 1 + d1 u1 (col differences)
-    atomicAdd(d0 + rhi * W + c, sr * g_G00); atomicAdd(d0 + rlo * W + c, -sr * g_G00);
-    atomicAdd(d1 + rhi * W + c, sr * g_G10); atomicAdd(d1 + rlo * W + c, -sr * g_G10);
-    atomicAdd(d0 + r * W + chi, sc * g_G01); atomicAdd(d0 + r * W + clo, -sc * g_G01);
-    atomicAdd(d1 + r * W + chi, sc * g_G11); atomicAdd(d1 + r * W + clo, -sc * g_G11);
+    red_add(d0 + rhi * W + c, sr * g_G00); red_add(d0 + rlo * W + c, -sr * g_G00);
+    red_add(d1 + rhi * W + c, sr * g_G10); red_add(d1 + rlo * W + c, -sr * g_G10);
+    red_add(d0 + r * W + chi, sc * g_G01); red_add(d0 + r * W + clo, -sc * g_G01);
+    red_add(d1 + r * W + chi, sc * g_G11); red_add(d1 + r * W + clo, -sc * g_G11);
   }
 }
 

@@ -10,6 +10,7 @@ trajectory (``b2_shoot_bwd``).
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 from torch.autograd.function import once_differentiable
@@ -29,6 +30,15 @@ _flags = {"fwd": 0, "bwd": 0}
 # of the fused adjoint kernel where that exists (square grids up to 128x128); False runs them as separate kernels
 # through a gradient image (always the case at 256x256, on the op-level path, or when dL/dsrc is wanted).
 fuse_seeds = True
+# 256x256 inference: a 4-SM cluster has to sit inside one GPC, so the fused cluster kernel leaves SMs without a CTA
+# (33 clusters, 16 idle SMs on a 148-SM B200).  With `idle_sm_split` the last slices of a batch go through the op-level
+# kernel sequence on a second stream: the persistent cluster kernel is launched first and owns its SMs, so the
+# op-level kernels land on exactly the stranded ones.  `idle_sm_pair_cost` = time of one op-level pair on 16 idle SMs in
+# units of one cluster's time per pair (measured on B200); the split minimises the longer arm.
+idle_sm_split = True
+idle_sm_pair_cost = 0.23
+_side_streams = {}
+_cluster_occ = {}
 
 
 @contextlib.contextmanager
@@ -75,9 +85,64 @@ def _alloc_outputs(P, B, T1, H, W, dev, want, v0_is_momentum, n_sectors, n_frame
     return out
 
 
+def _idle_split_slices(B, T1, dev):
+    """Trailing slices of a 256x256 inference batch that go to the op-level path on the SMs the clusters strand
+    (0 = no split): minimise max(rounds of the cluster kernel, op-level time), both in units of one cluster round."""
+    if not idle_sm_split or B < 2:
+        return 0
+    occ = _cluster_occ.get(dev.index)
+    if occ is None:
+        n, idle = C.c_int(0), C.c_int(0)
+        check(lib().b2_shoot_cluster_occupancy(C.byref(n), C.byref(idle)), "b2_shoot_cluster_occupancy")
+        occ = _cluster_occ[dev.index] = (n.value, idle.value)
+    ncl, idle = occ
+    if ncl < 1 or idle < 4:
+        return 0
+    cost = idle_sm_pair_cost * 16.0 / idle
+    whole = math.ceil(B * T1 / ncl)
+    best, best_t = 0, float(whole)
+    for b2 in range(1, B // 2 + 1):
+        t = max(math.ceil((B - b2) * T1 / ncl), b2 * T1 * cost)
+        if t < best_t:
+            best, best_t = b2, t
+    return best if best_t <= 0.97 * whole else 0
+
+
+def _launch_shoot_split(b2, v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
+                        B, T1, want, src_per_pair, src_ss, tar_ss):
+    """256x256 inference with the last ``b2`` slices on the op-level path (second stream, idle SMs); the outputs are
+    one set of slice-major tensors, each arm writes its own rows.  ``src`` / ``tar``: the strided cine views."""
+    P, _, H, W = v0.shape
+    dev = v0.device
+    out = _alloc_outputs(P, B, T1, H, W, dev, want, False, n_sectors, n_frames, num_steps, False)
+    B1 = B - b2
+
+    def rows(lo, hi):
+        return {k: (t[lo:hi] if k in ("S", "counts") else t[lo * T1:hi * T1]) for k, t in out.items()}
+
+    cur = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(dev)
+    ready = cur.record_event()                       # inputs complete
+    _launch_shoot(v0[:B1 * T1], src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
+                  B1, T1, want, False, src_per_pair, False, out=rows(0, B1), src_slice_stride=src_ss,
+                  tar_slice_stride=tar_ss)
+    side.wait_event(ready)
+    with torch.cuda.stream(side):
+        src2 = src[B1:].reshape(b2 * T1, 1, H, W).contiguous() if src_per_pair else src[B1:].contiguous()
+        tar2 = tar[B1:].reshape(b2 * T1, 1, H, W).contiguous()
+        mom2 = moments[B1:].contiguous() if moments is not None else None
+        _launch_shoot(v0[B1 * T1:], src2, tar2, mom2, frame, metric, num_steps, T, background, n_sectors, n_frames,
+                      b2, T1, want, False, src_per_pair, False, out=rows(B1, B), first_slice=B1,
+                      flags=_lib.FLAG_OPLEVEL)
+    cur.wait_stream(side)
+    return out
+
+
 def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
                   B, T1, want, v0_is_momentum, src_per_pair, save_traj, out=None, ws=None,
-                  src_slice_stride=0, tar_slice_stride=0, first_slice=0):
+                  src_slice_stride=0, tar_slice_stride=0, first_slice=0, flags=None):
     """Run ``b2_shoot_fwd``; outputs are allocated here unless ``out`` (contiguous tensors) is given.
     ``frame``: :class:`strain.Frame` of the batch (``first_slice`` = offset of this launch's slices in it) or None.
     The caller has made the tensors' device current (``_lib.device_guard`` / ``on_device``)."""
@@ -92,7 +157,7 @@ def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background
     if frame is not None:
         fs = frame.c_struct(first_slice)
         a.table, a.table_slice_stride, a.theta0, a.clockwise = fs.table, fs.table_slice_stride, fs.theta0, fs.clockwise
-    a.flags = _flags["fwd"]
+    a.flags = _flags["fwd"] if flags is None else flags
     for k in ("m0", "vel", "u", "sdef", "S", "counts", "traj", "loss_terms"):
         setattr(a, k, out[k].data_ptr() if k in out else None)
     a.B, a.T1, a.H, a.W = B, T1, H, W
@@ -106,7 +171,7 @@ def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background
     if ws is None or ws.numel() < nbytes:
         ws = _workspace(nbytes, dev)
     check(lib().b2_shoot_fwd(C.byref(a), ptr(ws), ws.numel(), stream()), "b2_shoot_fwd")
-    fused = _fused_size(H, W)                        # one persistent kernel (256: one 4-CTA cluster per pair)
+    fused = _fused_size(H, W) and not a.flags        # one persistent kernel (256: one 4-CTA cluster per pair)
     _lib.count_launch(1 if fused else 3 + 3 * int(num_steps) + 2)   # path B: flat, 3 kernels per step, warp, strain
     return out
 
@@ -200,10 +265,17 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         require_cuda(v0)
         require_cuda(src if src_ss == 0 else None, tar if tar_ss == 0 else None)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        out = _launch_shoot(v0, src, tar, moments if with_strain else None, frame if with_strain else None, metric,
-                            num_steps, T, background, n_sectors, n_frames, B, T1,
-                            {"m0": True, "vel": True, "sdef": True, "S": with_strain, "loss_terms": with_loss}, False,
-                            src_per_pair, need, src_slice_stride=src_ss, tar_slice_stride=tar_ss)
+        want = {"m0": True, "vel": True, "sdef": True, "S": with_strain, "loss_terms": with_loss}
+        H, W = v0.shape[-2:]
+        b2 = _idle_split_slices(B, T1, v0.device) if (H == 256 and _fused_size(H, W) and not need and src_ss) else 0
+        if b2:
+            out = _launch_shoot_split(b2, v0, src, tar, moments if with_strain else None,
+                                      frame if with_strain else None, metric, num_steps, T, background, n_sectors,
+                                      n_frames, B, T1, want, src_per_pair, src_ss, tar_ss)
+        else:
+            out = _launch_shoot(v0, src, tar, moments if with_strain else None, frame if with_strain else None, metric,
+                                num_steps, T, background, n_sectors, n_frames, B, T1, want, False,
+                                src_per_pair, need, src_slice_stride=src_ss, tar_slice_stride=tar_ss)
         ctx.cfg = (metric, num_steps, T, background, n_sectors, n_frames, B, T1, src_per_pair, with_strain,
                    src_ss, tar_ss)
         ctx.set_materialize_grads(False)      # unused outputs arrive as None in backward, not as zero tensors

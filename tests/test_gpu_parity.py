@@ -1296,3 +1296,51 @@ def test_fused_seeds_match_seed_kernels(pkg, oracle, dev, cfg):
                 f"fused={fused} loss_terms={loss_terms}: {relerr(vg.grad, vd.grad):.2e} (oracle32 vs 64: {own:.2e})"
         assert relerr(grads[True][0], grads[False][0]) < 5e-5, f"{relerr(grads[True][0], grads[False][0]):.2e}"
         assert grads[True][1] < grads[False][1]              # fewer launches of our kernels
+
+
+@pytest.mark.parametrize("shared_src", [True, False])
+def test_idle_sm_split_matches_unsplit_and_oracle(pkg, oracle, dev, shared_src):
+    """256x256 inference with the trailing slices on the op-level path (second stream, the SMs the 4-CTA clusters
+    strand): the same outputs as the unsplit cluster launch to fp32 round-off, bit-equal member counts through the
+    per-slice sector frame, every slice within TOL of the oracle; the automatic split only engages when it pays."""
+    sh = pkg.shooting
+    B, T, H, S = 3, 4, 256, 4
+    vol = pkg.synthetic.synthetic_masks(B, T, H, H, seed=11).to(dev)
+    src_vol, tar_vol = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    if not shared_src:
+        src_vol = src_vol.contiguous()
+    v0 = _smooth_v0(pkg, B * (T - 1), H, H, 5, 3.0)
+    th, cw = [0.0, 0.7, -1.1], [True, False, True]
+    saved = sh._idle_split_slices
+    outs = {}
+    try:
+        for b2 in (0, 1):
+            sh._idle_split_slices = (lambda n: (lambda B_, T1_, dev_: n))(b2)
+            with torch.no_grad():
+                outs[b2] = pkg.shoot_warp_strain(v0.to(dev), src_vol, tar_vol, pkg.FluidMetric(PARAMS), num_steps=S,
+                                                 loss_terms=True, theta0=th, clockwise=cw)
+        torch.cuda.synchronize()
+    finally:
+        sh._idle_split_slices = saved
+    keys = ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix", "registration_loss_terms")
+    # the warped source is a BINARY mask: its error is |du| in pixels times a unit jump (3e-5 as in the multi-wave test);
+    # the squared-error term of the loss sums it over the image
+    tol = {"deformed_source": 3e-5, "registration_loss_terms": 3e-5}
+    for k in keys:
+        assert relerr(outs[1][k], outs[0][k]) < tol.get(k, TOL), f"{k}: {relerr(outs[1][k], outs[0][k]):.2e}"
+    ref = oracle.forward_volume(v0, src_vol.cpu(), tar_vol.cpu(), oracle.FluidMetric(PARAMS), S, theta0=th, clockwise=cw)
+    for k in keys[:5]:
+        assert relerr(outs[1][k], ref[k]) < tol.get(k, TOL), f"{k} vs oracle: {relerr(outs[1][k], ref[k]):.2e}"
+        assert relerr(outs[1][k][-1:], ref[k][-1:]) < tol.get(k, TOL), f"{k} (op-level arm) vs oracle"
+    # the planner: nothing to split for one slice or a batch that fills whole rounds; a real share otherwise
+    assert sh._idle_split_slices(1, 49, dev) == 0
+    b2 = sh._idle_split_slices(256, 49, dev)
+    assert 0 <= b2 <= 64
+    # a differentiable call never splits (the adjoint needs the trajectory of every pair in one layout)
+    vg = v0.to(dev).requires_grad_(True)
+    sh._idle_split_slices = lambda *a: (_ for _ in ()).throw(AssertionError("split consulted on the training path"))
+    try:
+        pkg.shoot_warp_strain(vg, src_vol, tar_vol, pkg.FluidMetric(PARAMS), num_steps=2)["displacement"].sum().backward()
+    finally:
+        sh._idle_split_slices = saved
+    assert torch.isfinite(vg.grad).all()
