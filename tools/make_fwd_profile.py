@@ -50,11 +50,15 @@ def main(raw_csv, cs_csv, launches_csv, event_ms):
     hi = next(i for i, r in enumerate(lr) if r and r[0] == "ID")
     ik, iv = lr[hi].index("Kernel Name"), lr[hi].index("Metric Value")
     agg = collections.defaultdict(lambda: [0, 0.0])
+    fwd_max = max((float(r[iv].replace(",", "")) for r in lr[hi + 1:] if len(r) > iv and "shoot_fwd" in r[ik]), default=0.0)
     for r in lr[hi + 1:]:
         if len(r) > iv:
-            a = agg[r[ik].split("(")[0][:60]]
+            name, dur = r[ik].split("(")[0][:60], float(r[iv].replace(",", ""))
+            if "shoot_fwd" in name:      # whole resident steps vs the quarter-batch chunks of the host-buffer pipeline
+                name += " [1536 pairs, resident step]" if dur > 0.6 * fwd_max else " [384-pair chunk of the host pipeline]"
+            a = agg[name]
             a[0] += 1
-            a[1] += float(r[iv].replace(",", ""))
+            a[1] += dur
     tot = sum(a[1] for a in agg.values())
     ll = "\n".join(f"| `{k}` | {a[0]} | {a[1] / a[0] / 1e6:.3f} | {100 * a[1] / tot:.1f} % |"
                    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:6])
@@ -89,7 +93,11 @@ Launch list of the timed region (`r02_launches.csv`; cold-cache, serialised):
 What changed against round 1: the second radix pass of the forward column FFT, the symbol multiply and the first radix pass
 of the inverse column FFT run in registers on mirror-closed pairs of tasks (`fluid_cols_mid_fused`, DESIGN.md section 4):
 two shared-memory round trips of the field (shared-memory wavefronts 505 M -> {float(m['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'][1]) / 1e6:.0f} M), two of nine barriers and the multiplier's
-index arithmetic less per operator: 2.575 G -> {float(m['smsp__inst_executed.sum'][1]) / 1e9:.3f} G warp instructions.
+index arithmetic less per operator: 2.575 G -> {float(m['smsp__inst_executed.sum'][1]) / 1e9:.3f} G warp instructions.  And the
+1536 pairs no longer run as 10.38 static rounds on the 148 persistent CTAs: work is drawn from one atomic ticket counter,
+whole pairs first, then the last 148 pairs in chunks of two EPDiff steps that any CTA can continue from the pair's
+(u_s, m0) in the scratch (flag + fence hand-over, DESIGN.md section 4) - the kernel ends within one chunk of perfect
+balance instead of one pair (3.42 -> 3.28 ms).
 
 Per-source-line roll-up (`tools/ncu_lines.py`; share of stall samples / of executed warp instructions, dominant stalls):
 
@@ -97,7 +105,7 @@ Per-source-line roll-up (`tools/ncu_lines.py`; share of stall samples / of execu
 {lines}
 ```
 
-Reading: still issue-bound (65 % of issue slots, DRAM 4.5 %, L2 11 %).  `fft.cuh` is 49 % of the instructions (radix
+Reading: still issue-bound (two thirds of the issue slots, DRAM 5 %, L2 11 %).  `fft.cuh` is 49 % of the instructions (radix
 butterflies with compile-time twiddles; 7 shared-memory round trips per operator are left and each of them sits between
 two transposing passes, i.e. cannot be fused in registers), the two bilinear gathers (`common.cuh`) 31 %.  Barrier
 stalls rose from 8 % to 13 % of the samples: the fused middle is the longest uninterrupted phase, so arrival times at
