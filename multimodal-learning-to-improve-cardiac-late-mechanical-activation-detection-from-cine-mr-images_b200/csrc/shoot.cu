@@ -866,6 +866,43 @@ static int64_t fused_bwd_grid(int64_t P, int64_t H) {
   return g < P ? g : P;
 }
 
+#ifndef B2_BWD_L2_PERSIST
+#define B2_BWD_L2_PERSIST 0
+#endif
+// Optional: pin the per-CTA scratch of the adjoint in L2 (persisting access-policy window on the launch stream) so
+// that the streaming trajectory does not evict it.  Returns true when a window was set (reset after the launch).
+static bool l2_window_set(cudaStream_t st, void* base, size_t bytes) {
+#if B2_BWD_L2_PERSIST
+  static int max_persist = -1, max_window = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (max_persist < 0) {
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) max_persist = 0;
+    if (cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess) max_window = 0;
+    if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) max_persist = 0;
+    (void)cudaGetLastError();
+  }
+  if (max_persist <= 0 || max_window <= 0) return false;
+  cudaStreamAttrValue v = {};
+  v.accessPolicyWindow.base_ptr = base;
+  v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+  const double r = (double)max_persist / (double)v.accessPolicyWindow.num_bytes;
+  v.accessPolicyWindow.hitRatio = r < 1.0 ? (float)r : 1.0f;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return true;
+#else
+  (void)st; (void)base; (void)bytes;
+  return false;
+#endif
+}
+static void l2_window_reset(cudaStream_t st) {
+  cudaStreamAttrValue v = {};
+  v.accessPolicyWindow.num_bytes = 0;
+  (void)cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 template <int H, int W, int NT>
 static int launch_fused_bwd(const ShootBwdParams& prm_in, int background, cudaStream_t st) {
   const size_t smem = BwdSmem<H, W>::bytes;
@@ -882,6 +919,7 @@ static int launch_fused_bwd(const ShootBwdParams& prm_in, int background, cudaSt
     prm.flags = reinterpret_cast<int*>(tk + 16);
     B2_CUDA(cudaMemsetAsync(tk, 0, 16 + sizeof(int) * (size_t)grid * kBwdMaxChunks, st));
   }
+  const bool win = l2_window_set(st, prm.scratch, sizeof(float) * (size_t)grid * 3 * prm.field);
   if (background == B2_BG_CLAMP) {
     B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     shoot_bwd_kernel<H, W, NT, B2_BG_CLAMP><<<(unsigned)grid, NT, smem, st>>>(prm);
@@ -889,6 +927,7 @@ static int launch_fused_bwd(const ShootBwdParams& prm_in, int background, cudaSt
     B2_CUDA(cudaFuncSetAttribute(shoot_bwd_kernel<H, W, NT, B2_BG_ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     shoot_bwd_kernel<H, W, NT, B2_BG_ZERO><<<(unsigned)grid, NT, smem, st>>>(prm);
   }
+  if (win) l2_window_reset(st);
   B2_CHECK_LAUNCH();
   return B2_OK;
 }
