@@ -45,10 +45,12 @@ def test_struct_sizes_match_header(pkg):
     L = pkg._lib.lib()
     assert L.b2_sizeof_shoot_args() == ctypes.sizeof(pkg._lib.ShootArgs)
     assert L.b2_sizeof_shoot_bwd_args() == ctypes.sizeof(pkg._lib.ShootBwdArgs)
-    # the adjoint workspace is sized per path: fused (resident CTAs x 3 fields) far below op-level (5 P fields)
+    # the adjoint workspace is sized per path: fused (resident CTAs x 3 fields, as much again for the tail pairs of the
+    # dynamic schedule, ticket + flags) far below op-level (5 P fields)
     fused = L.b2_shoot_bwd_workspace_bytes_flags(1536, 128, 128, 0)
     oplevel = L.b2_shoot_bwd_workspace_bytes_flags(1536, 128, 128, pkg._lib.FLAG_OPLEVEL)
-    assert 0 < fused < oplevel / 10 and oplevel >= 5 * 1536 * 2 * 128 * 128 * 4
+    assert 0 < fused < oplevel / 8 and oplevel >= 5 * 1536 * 2 * 128 * 128 * 4
+    assert fused >= 2 * 148 * 3 * 2 * 128 * 128 * 4
     assert L.b2_shoot_bwd_workspace_bytes(1536, 128, 128) == fused
     assert L.b2_shoot_bwd_workspace_bytes_flags(4, 100, 100, 0) > 0     # op-level sized; rejected at call time (FFT size)
 
