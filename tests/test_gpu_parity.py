@@ -1010,6 +1010,89 @@ def test_multiwave_backward(pkg, oracle, dev):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Dynamic ticket schedule of the single-CTA kernels: engaged when P >= 2 x grid and S >= 4
+# ------------------------------------------------------------------------------------------------------------------
+def _grid_of(pkg, H):
+    """Upper bound of the persistent grid at this size: SMs x the most CTAs one SM can hold."""
+    sms = pkg._lib.lib().b2_device_sm_count(0)
+    return sms * {16: 16, 32: 8, 64: 6, 128: 1}[H]
+
+
+@pytest.mark.parametrize("H,S", [(16, 5), (32, 7), (64, 4), (128, 5), (128, 10)])
+def test_dynamic_schedule_forward_is_bit_identical_to_static(pkg, dev, H, S):
+    """Whole batch (ticket schedule: the last `grid` pairs run as chunks of two EPDiff steps handed from CTA to CTA
+    through global memory) against the same pairs in launches too small to engage it (static schedule): every output
+    bit-identical - the forward has no float atomics - including odd step counts (the last chunk takes the
+    remainder) and two runs of the whole batch against each other."""
+    T = 26 if H >= 64 else 101
+    T1 = T - 1
+    B = -(-(2 * _grid_of(pkg, H) + 40) // T1)
+    vol = pkg.synthetic.synthetic_masks(B, T, H, H, seed=7).to(dev)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    v0 = _smooth_v0(pkg, B * T1, H, H, 71, 2.0 if H < 64 else 3.0).to(dev)
+    m = pkg.FluidMetric(PARAMS)
+    keys = ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix", "registration_loss_terms")
+    with torch.no_grad():
+        full = pkg.shoot_warp_strain(v0, sv, tv, m, num_steps=S, loss_terms=True)
+        again = pkg.shoot_warp_strain(v0, sv, tv, m, num_steps=S, loss_terms=True)
+        for k in keys:
+            assert torch.equal(full[k], again[k]), f"{k}: run-to-run"
+        nb = max(1, 140 // T1)                       # slices per small launch: fewer pairs than one grid
+        for b0 in list(range(0, B, nb))[-max(3, (B // nb) // 4):] + [0]:     # the tail pairs live in the LAST slices
+            b1 = min(B, b0 + nb)
+            part = pkg.shoot_warp_strain(v0[b0 * T1:b1 * T1], sv[b0:b1], tv[b0:b1], m, num_steps=S, loss_terms=True)
+            for k in keys:
+                f = full[k][b0:b1] if k in ("strain_matrix", "deformed_source") else full[k][b0 * T1:b1 * T1]
+                assert torch.equal(f, part[k]), f"{k}: slices {b0}..{b1} differ between the schedules"
+
+
+@pytest.mark.parametrize("H,S", [(16, 5), (64, 4), (128, 5), (128, 10)])
+def test_dynamic_schedule_adjoint_matches_static(pkg, oracle, dev, H, S):
+    """Fused adjoint with the ticket schedule (P >= 2 x grid: the tail pairs' reverse sweep is handed over between CTAs
+    through their own scratch fields) against the same pairs in small launches (static schedule); the accumulators
+    take float REDs, so the bound is round-off (1e-5 of the gradient scale), not bit equality.  At 128x128 the last
+    slice is also held to autograd through the oracle."""
+    T = 26 if H >= 64 else 101
+    T1 = T - 1
+    B = -(-(2 * _grid_of(pkg, H) + 40) // T1)
+    vol = pkg.synthetic.synthetic_masks(B, T, H, H, seed=9)
+    sv, tv = pkg.data.split_vol_to_registration_pairs(vol.to(dev), "Lagrangian", 3)
+    v0 = _smooth_v0(pkg, B * T1, H, H, 72, 2.0 if H < 64 else 3.0)
+    Sgt = 0.05 * _rand(B, 1, 126, 40, seed=73)
+    m = pkg.FluidMetric(PARAMS)
+    n_tar, n_S = tv.numel(), Sgt.numel()
+
+    def loss(out, tar, sgt):       # sums with the WHOLE batch's normalisation: the gradient of a slice's pairs is local
+        return 0.5 * ((tar - out["deformed_source"]) ** 2).sum() / n_tar / 0.03 ** 2 \
+            + 0.1 * (out["velocity"] * out["momentum"]).sum() / n_tar + 1000.0 * ((out["strain_matrix"] - sgt) ** 2).sum() / n_S
+
+    vg = v0.to(dev).requires_grad_(True)
+    loss(pkg.shoot_warp_strain(vg, sv, tv, m, num_steps=S), tv, Sgt.to(dev)).backward()
+    g_full = vg.grad
+    scale = float(g_full.abs().max())
+    nb = max(1, 140 // T1)
+    for b0 in list(range(0, B, nb))[-max(3, (B // nb) // 4):] + [0]:
+        b1 = min(B, b0 + nb)
+        vp = v0[b0 * T1:b1 * T1].to(dev).requires_grad_(True)
+        loss(pkg.shoot_warp_strain(vp, sv[b0:b1], tv[b0:b1], m, num_steps=S), tv[b0:b1], Sgt[b0:b1].to(dev)).backward()
+        err = float((g_full[b0 * T1:b1 * T1] - vp.grad).abs().max()) / scale
+        assert err < 1e-5, f"slices {b0}..{b1}: {err:.2e}"
+    if H == 128:
+        src_vol, tar_vol = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+        # binary masks put kinks into this loss (bilinear taps of a 0/1 image, sector membership): the fp32 oracle is
+        # itself ~1e-4 from its float64 run, so the CUDA gradient is held to float64 within three times that
+        gref = {}
+        for dt in (torch.float32, torch.float64):
+            vc = v0[-T1:].to(dt).clone().requires_grad_(True)
+            loss(oracle.forward_volume(vc, src_vol[-1:].to(dt), tar_vol[-1:].to(dt), oracle.FluidMetric(PARAMS), S),
+                 tar_vol[-1:].to(dt), Sgt[-1:].to(dt)).backward()
+            gref[dt] = vc.grad
+        own = relerr(gref[torch.float32], gref[torch.float64])
+        err = relerr(g_full[-T1:].cpu().double(), gref[torch.float64])
+        assert err < max(1e-4, 3.0 * own), f"{err:.2e} (fp32 oracle vs float64: {own:.2e})"
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # Sector frame: per-slice theta0 + direction (DENSE_utils.py:196-204 of the reference)
 # ------------------------------------------------------------------------------------------------------------------
 def test_sector_frame_matches_reference_mesh_on_gpu(pkg, dev):
