@@ -402,6 +402,22 @@ __device__ __forceinline__ void fft_fwd_pass1(float2* __restrict__ z, const floa
   }
   __syncthreads();
 }
+// second pass of a forward transform on its own (the cluster kernels run the first one on operands pulled over DSMEM)
+template <int N, int NL, int NT, int ES, int LS>
+__device__ __forceinline__ void fft_fwd_pass2(float2* __restrict__ z, int tid) {
+  constexpr int N1 = Fact<N>::N1, N2 = Fact<N>::N2;
+  for (int t = tid; t < NL * N1; t += NT) {
+    const int line = t % NL, k1 = t / NL;
+    float2* base = z + line * LS + (N2 * k1) * ES;
+    float2 y[N2];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) y[n2] = base[n2 * ES];
+    DftReg<N2, -1>::run(y);
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) base[k2 * ES] = y[k2];
+  }
+  __syncthreads();
+}
 template <int N, int NL, int NT, int ES, int LS>
 __device__ __forceinline__ void fft_inv_pass2(float2* __restrict__ z, int tid) {
   constexpr int N1 = Fact<N>::N1, N2 = Fact<N>::N2;

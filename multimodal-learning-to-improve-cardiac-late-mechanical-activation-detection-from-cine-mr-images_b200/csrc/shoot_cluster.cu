@@ -58,9 +58,35 @@ __device__ __forceinline__ int zs_row(int r) {
   return (lr < half ? 0 : kCN / 2 - half * kCW) + x * (half * kCW) + lr * kCW;
 }
 
+#ifndef B2_CLUSTER_DSMEM
+#define B2_CLUSTER_DSMEM 0     // 1: row <-> column exchange over distributed shared memory (measured: 16.55 vs 11.87 ms)
+#endif
+// ---- distributed shared memory: the slab of CTA g of this cluster, read in place
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned dsmem_of_rank(unsigned addr, int rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float2 ld_dsmem2(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+// home of spectrum-cell block b (16 cells): CTA g, local block q  <->  c_group_block[g][q] == b
+__device__ __forceinline__ void block_home(int b, int& g, int& q) {
+  g = 0; q = 0;
+#pragma unroll
+  for (int gg = 0; gg < kCL; ++gg)
+#pragma unroll
+    for (int qq = 0; qq < 16 / kCL; ++qq)
+      if (c_group_block[gg][qq] == b) { g = gg; q = qq; }
+}
+
 // One fluid operator on the slab in z (row layout in, row layout out): row FFT -> spectrum exchange through the
 // per-cluster L2 scratch Zs -> column FFT of a mirror-closed column group -> multiplier -> inverse, same way back.
 // A plain inlined function (a by-reference lambda put its closure in local memory).
+#if !B2_CLUSTER_DSMEM
 template <bool inverse>
 __device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2* __restrict__ z, const float2* tw,
                                               const float2* cs, float2* Zs, const FluidParams fp, const int tid,
@@ -119,6 +145,104 @@ __device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2
   __syncthreads();
   fft_lines<256, kSR, +1, kCNT, 1, kLDR>(z, tw, tid);
 }
+
+#else
+// Same operator with the row <-> column exchange over DISTRIBUTED SHARED MEMORY and no staging buffer: the first radix
+// pass of the column FFT pulls its 16 operands per thread straight out of the four CTAs' row-layout slabs
+// (ld.shared::cluster: rows n2 + 16 n1 of column pc live in CTA n1 / 4), and the first radix pass of the inverse row
+// FFT pulls its 16 operands (the cells of block k1 of its row) out of the column-layout slab of the CTA that owns that
+// block.  Each pull sits between two cluster barriers: one before (the producers' pass is complete everywhere), one
+// after the butterflies (every CTA has its operands in registers: the slabs may be overwritten in the new layout).
+// Against the L2 exchange this removes, per exchange, a 128 KiB store + 128 KiB load per CTA through L2, two
+// shared-memory passes and the wait for the stores inside the barrier's release fence; it adds one cluster barrier.
+// MEASURED AND REJECTED (parity green, 784 pairs): forward 16.55 ms against 11.87 ms with the L2 exchange, training step
+// 43.2 against 34.0 ms - 8-byte pulls over the SM-to-SM network run at a few bytes per clock per SM, far below what
+// the same data achieves as coalesced 128-byte lines through L2.  Kept as a compile-time option for the record.
+template <bool inverse>
+__device__ __forceinline__ void cluster_fluid(cg::cluster_group& cluster, float2* __restrict__ z, const float2* tw,
+                                              const float2* cs, float2* /*Zs: unused*/, const FluidParams fp, const int tid,
+                                              const int rk, const int r0, const int c, const int br, const int lc,
+                                              const int q, const int pc) {
+  constexpr int H = kCH, W = kCW, N1 = 16, N2 = 16, per = kSR / 16;
+  static_assert(kSR * N2 == kCNT && kSR * N1 == kCNT, "one radix-16 task per thread in both pulled passes");
+  (void)c; (void)br;
+  fft_lines<256, kSR, -1, kCNT, 1, kLDR>(z, tw, tid);
+  const unsigned zb = smem_u32(z);
+  cluster.sync();                                   // row FFTs complete in all slabs
+  {
+    const int n2 = tid / kSR;                       // column lc (cell pc), input rows n2 + 16 n1
+    float2 x[N1];
+#pragma unroll
+    for (int g = 0; g < kCL; ++g) {
+      const unsigned rb = dsmem_of_rank(zb, g) + (unsigned)((n2 * kLDR + pc) * (int)sizeof(float2));
+#pragma unroll
+      for (int j = 0; j < per; ++j) x[g * per + j] = ld_dsmem2(rb + (unsigned)(16 * j * kLDR * (int)sizeof(float2)));
+    }
+    DftReg<N1, -1>::run(x);
+#pragma unroll
+    for (int k1 = 1; k1 < N1; ++k1) {
+      const float2 w = tw[n2 * k1];
+      x[k1] = cmul(x[k1], w.x, -w.y);
+    }
+    cluster.sync();                                 // every CTA holds its operands: the slab is free for the column layout
+    float2* base = z + lc + n2 * kLDC;
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) base[(N2 * k1) * kLDC] = x[k1];
+  }
+  __syncthreads();
+  fft_fwd_pass2<256, kSR, kCNT, kLDC, 1>(z, tid);
+  {
+    const int k1 = cell_to_freq<256>(pc);
+    const int qcell = freq_to_cell<256>((W - k1) & (W - 1));
+    const int lc2 = mirror_q(rk, q) * 16 + (qcell & 15);
+    const float2 cs1 = cs[k1];
+    const float h = 0.5f * fp.scale, bs1 = fp.beta * cs1.y;
+    for (int k0 = tid / kSR; k0 <= H / 2; k0 += kCNT / kSR) {
+      const int pr = freq_to_cell<256>(k0), qr = freq_to_cell<256>((H - k0) & (H - 1));
+      if (pr == qr && pc > qcell) continue;
+      const float2 cs0 = cs[k0];
+      const float lam = fp.gamma + fp.alpha * (cs0.x + cs1.x);
+      const float L00 = lam + fp.beta * cs0.x, L11 = lam + fp.beta * cs1.x, L01 = cs0.y * bs1;
+      float A, Br, Bi;
+      if (inverse) {
+        const float idet = __fdividef(h, L00 * L11 - L01 * L01);
+        A = idet * (L11 + L00); Br = idet * (L11 - L00); Bi = -2.0f * idet * L01;
+      } else {
+        A = h * (L00 + L11); Br = h * (L00 - L11); Bi = 2.0f * h * L01;
+      }
+      float2* zp = z + pr * kLDC + lc;
+      float2* zq = z + qr * kLDC + lc2;
+      const float2 Z = *zp, Zq = *zq;
+      *zp = make_float2(A * Z.x + Br * Zq.x + Bi * Zq.y, A * Z.y + Bi * Zq.x - Br * Zq.y);
+      if (zp != zq) *zq = make_float2(A * Zq.x + Br * Z.x + Bi * Z.y, A * Zq.y + Bi * Z.x - Br * Z.y);
+    }
+    __syncthreads();
+  }
+  fft_lines<256, kSR, +1, kCNT, kLDC, 1>(z, tw, tid);
+  cluster.sync();                                   // inverse column FFTs complete in all column groups
+  {
+    const int line = tid % kSR, k1 = tid / kSR;     // row r0 + line, cells 16 k1 .. 16 k1 + 15 = block k1
+    int hg, hq;
+    block_home(k1, hg, hq);
+    const unsigned rb = dsmem_of_rank(zb, hg) + (unsigned)(((r0 + line) * kLDC + hq * 16) * (int)sizeof(float2));
+    float2 y[N2];
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) y[k2] = ld_dsmem2(rb + (unsigned)(k2 * (int)sizeof(float2)));
+    DftReg<N2, +1>::run(y);
+#pragma unroll
+    for (int n2 = 1; n2 < N2; ++n2) {
+      const float2 w = tw[n2 * k1];
+      y[n2] = cmul(y[n2], w.x, w.y);
+    }
+    cluster.sync();                                 // every CTA holds its operands: the slab is free for the row layout
+    float2* base = z + line * kLDR + N2 * k1;
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) base[n2] = y[n2];
+  }
+  __syncthreads();
+  fft_inv_pass2<256, kSR, kCNT, 1, kLDR>(z, tid);
+}
+#endif
 
 template <int BG, bool LOSS>
 __global__ void __launch_bounds__(kCNT, kCtasPerSM)
