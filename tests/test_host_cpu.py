@@ -71,6 +71,35 @@ def test_argument_errors_without_gpu(pkg):
         pkg.build_model({"type": "Nope"})
 
 
+def test_idle_sm_split_planner(pkg):
+    """Host logic of the 256x256 idle-SM split (shooting._idle_split_slices), no GPU: with 33 co-resident clusters
+    and 16 stranded SMs (a 148-SM B200) it hands over the slice counts measured best on the device (DESIGN.md
+    section 6), nothing when no SM is stranded or there is a single slice, and never more than half the batch."""
+    import torch
+    sh = pkg.shooting
+    dev = torch.device("cuda", 0)
+    saved = dict(sh._cluster_occ)
+    try:
+        sh._cluster_occ[0] = (33, 16)
+        assert sh._idle_split_slices(16, 49, dev) == 2
+        assert sh._idle_split_slices(32, 49, dev) == 3
+        assert 26 <= sh._idle_split_slices(256, 49, dev) <= 30
+        assert sh._idle_split_slices(1, 49, dev) == 0
+        for B in range(2, 40):
+            assert 0 <= sh._idle_split_slices(B, 24, dev) <= B // 2
+        sh._cluster_occ[0] = (37, 0)              # a device whose GPCs pack whole clusters: nothing to gain
+        assert sh._idle_split_slices(64, 49, dev) == 0
+        sh._cluster_occ[0] = (0, 0)               # clusters unavailable
+        assert sh._idle_split_slices(64, 49, dev) == 0
+        sh._cluster_occ[0] = (33, 16)
+        sh.idle_sm_split = False
+        assert sh._idle_split_slices(64, 49, dev) == 0
+    finally:
+        sh.idle_sm_split = True
+        sh._cluster_occ.clear()
+        sh._cluster_occ.update(saved)
+
+
 def test_shard_slices(pkg):
     for n in (1, 7, 64, 256):
         for ws in (1, 2, 3, 8):
