@@ -97,7 +97,8 @@ index arithmetic less per operator: 2.575 G -> {float(m['smsp__inst_executed.sum
 1536 pairs no longer run as 10.38 static rounds on the 148 persistent CTAs: work is drawn from one atomic ticket counter,
 whole pairs first, then the last 148 pairs in chunks of two EPDiff steps that any CTA can continue from the pair's
 (u_s, m0) in the scratch (flag + fence hand-over, DESIGN.md section 4) - the kernel ends within one chunk of perfect
-balance instead of one pair (3.42 -> 3.28 ms).
+balance instead of one pair (3.42 -> 3.28 ms).  Last, the radix-2 butterflies with non-trivial twiddles never form the
+product: `x0 = e + w o` as chained FMAs, `x1 = 2 e - x0` (6 instead of 8 instructions, `bfly16` in `fft.cuh`): 3.274 -> 3.245 ms.
 
 Per-source-line roll-up (`tools/ncu_lines.py`; share of stall samples / of executed warp instructions, dominant stalls):
 
