@@ -454,6 +454,9 @@ constexpr int kBwdUnrollB1 = B2_BWD_U1, kBwdUnrollB3a = B2_BWD_U3A, kBwdUnrollB3
 #ifndef B2_BWD_EVICT_FIRST
 #define B2_BWD_EVICT_FIRST 0
 #endif
+#ifndef B2_BWD_ROWWIN
+#define B2_BWD_ROWWIN 1   // sliding register window over the rows of a thread's column in the Ad* adjoint passes
+#endif
 // Trajectory loads of the adjoint with an L2 evict-first policy (createpolicy + ld.global.nc.L2::cache_hint): the
 // (u_s, v_s) entry streams through once per step, the scratch fields and m0 are what should stay in L2.
 __device__ __forceinline__ unsigned long long make_evict_first_policy() {
@@ -732,6 +735,12 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           prefetch_traj_l2<NT>(prm.traj + ((size_t)(2 * s - 2) * P + p) * prm.field,
                                prm.traj + ((size_t)(2 * s - 1) * P + p) * prm.field, (int)prm.field, tid);
         SplatCarry cy{-1, 0.f, 0.f};
+#if B2_BWD_ROWWIN
+        // the thread walks consecutive rows of one column: u_s(r-1), u_s(r), u_s(r+1) of that column slide through
+        // registers - two loads per row (the new row, both planes) instead of six; same values, same arithmetic
+        float ua_up = ldg_stream(us + max(rbase - 1, 0) * W + c, pol), ub_up = ldg_stream(us + N + max(rbase - 1, 0) * W + c, pol);
+        float ua_c = ldg_stream(us + rbase * W + c, pol), ub_c = ldg_stream(us + N + rbase * W + c, pol);
+#endif
 #pragma unroll (kBwdUnrollB3a)
         for (int k = 0; k < NB; ++k) {
           const int r = rbase + k, i = r * W + c;
@@ -741,12 +750,21 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
           const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
           const float sr = diff_scale(r, H);
+#if B2_BWD_ROWWIN
+          const float ua_dn = ldg_stream(us + odn, pol), ub_dn = ldg_stream(us + N + odn, pol);
+          const float d00 = sr * (ua_dn - ua_up), d10 = sr * (ub_dn - ub_up);
+          const float uc0 = ua_c, uc1 = ub_c;
+          ua_up = ua_c; ub_up = ub_c; ua_c = ua_dn; ub_c = ub_dn;
+          (void)oup;
+#else
           const float d00 = sr * (ldg_stream(us + odn, pol) - ldg_stream(us + oup, pol)), d10 = sr * (ldg_stream(us + N + odn, pol) - ldg_stream(us + N + oup, pol));
+          const float uc0 = ldg_stream(us + i, pol), uc1 = ldg_stream(us + N + i, pol);
+#endif
           const float d01 = sc * (ldg_stream(us + ort, pol) - ldg_stream(us + olf, pol)), d11 = sc * (ldg_stream(us + N + ort, pol) - ldg_stream(us + N + olf, pol));
           const float2 g = z[r * LD + c];
           const float gw0 = g.x + (d00 * g.x + d01 * g.y);
           const float gw1 = g.y + (d10 * g.x + d11 * g.y);
-          const Taps t = make_taps<BG>((float)r + ldg_stream(us + i, pol), (float)c + ldg_stream(us + N + i, pol), H, W);
+          const Taps t = make_taps<BG>((float)r + uc0, (float)c + uc1, H, W);
           splat2_agg<BG>(A, N, t, gw0, gw1, cy, lane);
           float w0, w1, o0, o1;
           {
@@ -774,6 +792,10 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
         }
         splat_flush(A, N, cy);
         __syncthreads();
+#if B2_BWD_ROWWIN
+        float qa_up = Qb[max(rbase - 1, 0) * W + c], qb_up = Qb[N + max(rbase - 1, 0) * W + c];
+        float qa_c = Qb[rbase * W + c], qb_c = Qb[N + rbase * W + c];
+#endif
 #pragma unroll (kBwdUnrollB3b)
         for (int k = 0; k < NB; ++k) {
           const int r = rbase + k, i = r * W + c;
@@ -784,9 +806,18 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           const float cmr = (r >= 1) ? diff_scale(r - 1, H) : 0.f, cpr = (r <= H - 2) ? diff_scale(r + 1, H) : 0.f;
           const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
           const float2 ql = z[r * LD + cl], qr = z[r * LD + cr];
+#if B2_BWD_ROWWIN
+          const float qa_dn = Qb[odn], qb_dn = Qb[N + odn];      // row-neighbour products slide through registers too
+          float o0 = (cmr * qa_up - cpr * qa_dn) + (cmc * ql.x - cpc * qr.x);
+          float o1 = (cmr * qb_up - cpr * qb_dn) + (cmc * ql.y - cpc * qr.y);
+          if (c0r != 0.f) { o0 += c0r * qa_c; o1 += c0r * qb_c; }                          // first / last image row
+          qa_up = qa_c; qb_up = qb_c; qa_c = qa_dn; qb_c = qb_dn;
+          (void)oup;
+#else
           float o0 = (cmr * Qb[oup] - cpr * Qb[odn]) + (cmc * ql.x - cpc * qr.x);
           float o1 = (cmr * Qb[N + oup] - cpr * Qb[N + odn]) + (cmc * ql.y - cpc * qr.y);
           if (c0r != 0.f) { o0 += c0r * Qb[i]; o1 += c0r * Qb[N + i]; }                    // first / last image row
+#endif
           if (c0c != 0.f) { const float2 qc = z[r * LD + c]; o0 += c0c * qc.x; o1 += c0c * qc.y; }   // first / last column
           __stcg(Gnext + i, gn0 + o0);
           __stcg(Gnext + N + i, gn1 + o1);
