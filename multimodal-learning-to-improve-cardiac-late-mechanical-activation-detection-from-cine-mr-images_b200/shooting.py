@@ -267,7 +267,9 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         want = {"m0": True, "vel": True, "sdef": True, "S": with_strain, "loss_terms": with_loss}
         H, W = v0.shape[-2:]
-        b2 = _idle_split_slices(B, T1, v0.device) if (H == 256 and _fused_size(H, W) and not need and src_ss) else 0
+        # (a stream capture keeps the plain single-stream launch)
+        b2 = _idle_split_slices(B, T1, v0.device) if (H == 256 and _fused_size(H, W) and not need and src_ss
+                                                      and not torch.cuda.is_current_stream_capturing()) else 0
         if b2:
             out = _launch_shoot_split(b2, v0, src, tar, moments if with_strain else None,
                                       frame if with_strain else None, metric, num_steps, T, background, n_sectors,
