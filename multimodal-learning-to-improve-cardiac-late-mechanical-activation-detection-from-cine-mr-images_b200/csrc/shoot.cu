@@ -21,6 +21,10 @@
 //
 // Backward: shoot_bwd_kernel (fused EPDiff adjoint, square grids up to 128x128), shoot_cluster_bwd_kernel (256x256,
 // shoot_cluster.cu) or the op-level sweep; b2_shoot_bwd_ex selects.
+//
+// Both single-CTA kernels draw their work from an atomic ticket counter (whole pairs, then the last grid-size pairs in
+// chunks of two steps handed from CTA to CTA through global memory) instead of a static round-robin: see
+// "dynamic schedule" below.
 #include "fft.cuh"
 #include "shoot_params.cuh"
 #include "strain.cuh"
@@ -63,10 +67,10 @@ constexpr int kComposeUnroll = B2_COMPOSE_UNROLL;
 
 struct ShootParams {
   b2_shoot_args a;
-  float* scratch;     // per-CTA: [u ping-pong | m0] fields; balanced schedule: + per-CTA hand-off [u_h | m0] + flags
+  float* scratch;     // per-CTA: [u ping-pong | m0] fields + hand-over field of the tail pair; then ticket + flags
   int64_t P;
   int64_t field;      // 2*H*W floats
-  int balanced;       // != 0: contiguous, equal-cost ranges of the pair timeline per CTA (split_schedule)
+  int balanced;       // != 0: dynamic ticket schedule with hand-over of the tail pairs (below)
 };
 
 // ---- dynamic schedule of the persistent grid (removes the partial last wave) ----------------------------------
