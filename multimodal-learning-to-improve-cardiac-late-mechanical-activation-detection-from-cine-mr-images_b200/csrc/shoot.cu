@@ -85,6 +85,18 @@ struct ShootParams {
 // earlier (normally finished; a flag per (pair, chunk) makes it a guarantee).  The CTA that holds an earlier ticket is
 // running, so waits cannot deadlock.  The kernel ends within one chunk of perfect balance instead of one pair, and
 // fast SMs simply draw more tickets.  Same arithmetic per pair whoever executes it: results are bit-identical.
+// v_s of the trajectory, the velocity output and the warped source are write-only in the forward kernel (the adjoint
+// / the caller read them much later): streaming stores keep them from displacing the L2-resident scratch
+#ifndef B2_TRAJ_STREAM
+#define B2_TRAJ_STREAM 1
+#endif
+#if B2_TRAJ_STREAM
+#define B2_TRAJ_STORE(p, v) __stcs((p), (v))
+#define B2_ONCE_LOAD(p) __ldcs(p)
+#else
+#define B2_TRAJ_STORE(p, v) (*(p) = (v))
+#define B2_ONCE_LOAD(p) __ldg(p)
+#endif
 #ifndef B2_BALANCED_BWD
 #define B2_BALANCED_BWD 1
 #endif
@@ -191,7 +203,9 @@ shoot_fwd_kernel(const ShootParams prm) {
 #pragma unroll 4
       for (int k = 0; k < NB; ++k) {
         const int r = k * RB + br;
-        z[r * LD + c] = make_float2(__ldg(f0 + r * W + c), __ldg(f0 + N + r * W + c));
+        // v0 is read once (streaming load); a momentum input is re-read by the gathers of every step
+        z[r * LD + c] = a.v0_is_momentum ? make_float2(__ldg(f0 + r * W + c), __ldg(f0 + N + r * W + c))
+                                         : make_float2(B2_ONCE_LOAD(f0 + r * W + c), B2_ONCE_LOAD(f0 + N + r * W + c));
       }
     }
     __syncthreads();
@@ -284,8 +298,8 @@ shoot_fwd_kernel(const ShootParams prm) {
           unext[N + i] = n.y;
           z[r * LD + c] = n;
           if (utraj0) { utraj0[i] = 0.f; utraj0[N + i] = 0.f; }
-          if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
-          if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+          if (velout) { B2_TRAJ_STORE(velout + i, v.x); B2_TRAJ_STORE(velout + N + i, v.y); }
+          if (vtraj) { B2_TRAJ_STORE(vtraj + i, v.x); B2_TRAJ_STORE(vtraj + N + i, v.y); }
           if (LOSS) acc_vm += v.x * m0g[i] + v.y * m0g[N + i];
         }
         if (LOSS) {
@@ -307,7 +321,7 @@ shoot_fwd_kernel(const ShootParams prm) {
           unext[i] = n.x;
           unext[N + i] = n.y;
           z[r * LD + c] = n;
-          if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+          if (vtraj) { B2_TRAJ_STORE(vtraj + i, v.x); B2_TRAJ_STORE(vtraj + N + i, v.y); }
         }
       }
       ucur = unext;
@@ -340,7 +354,7 @@ shoot_fwd_kernel(const ShootParams prm) {
         const int r = k * RB + br;
         const float2 u = z[r * LD + c];
         const float val = gather1_ldg<BG>(src, (float)r + u.x, (float)c + u.y, H, W);
-        if (sd) sd[r * W + c] = val;
+        if (sd) B2_TRAJ_STORE(sd + r * W + c, val);
         if (LOSS) {
           const float d = __ldg(tarp + r * W + c) - val;
           acc_sq += d * d;
@@ -861,8 +875,8 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
       const int r = rbase + k, i = r * W + c;
       float2 v = z[r * LD + c];
       if (prm.g_reg) { v.x += g2 * __ldg(radd + i); v.y += g2 * __ldg(radd + N + i); }
-      out[i] = v.x;
-      out[N + i] = v.y;
+      B2_TRAJ_STORE(out + i, v.x);
+      B2_TRAJ_STORE(out + N + i, v.y);
     }
     __syncthreads();
   }
