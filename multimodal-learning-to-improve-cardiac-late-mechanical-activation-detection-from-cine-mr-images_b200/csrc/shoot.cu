@@ -484,6 +484,17 @@ __device__ __forceinline__ unsigned long long make_evict_first_policy() {
 #endif
   return pol;
 }
+#ifndef B2_BWD_VS_STREAM
+#define B2_BWD_VS_STREAM 0     // 1: ld.global.cs for v_s - measured neutral (10.15 vs 10.15 ms per training step)
+#endif
+// v_s is read exactly once per adjoint step (u_s is gathered: its lines are re-used)
+__device__ __forceinline__ float ldg_once(const float* p) {
+#if B2_BWD_VS_STREAM
+  return __ldcs(p);
+#else
+  return __ldg(p);
+#endif
+}
 __device__ __forceinline__ float ldg_stream(const float* p, unsigned long long pol) {
 #if B2_BWD_EVICT_FIRST
   float v;
@@ -681,8 +692,8 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
 #pragma unroll
         for (int j = 0; j < kPipe; ++j) {
           const int i = (rbase + j) * W + c;
-          va[j] = ldg_stream(vs + i, pol);
-          vb[j] = ldg_stream(vs + N + i, pol);
+          va[j] = ldg_once(vs + i);
+          vb[j] = ldg_once(vs + N + i);
           asm volatile("prefetch.global.L1 [%0];" ::"l"(us + i));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(us + N + i));
         }
@@ -692,8 +703,8 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
           for (int j = 0; j < kPipe; ++j) {
             const int kn = min(k0 + kPipe + j, NB - 1);          // last group: harmless re-read of its own rows
             const int i = (rbase + kn) * W + c;
-            na[j] = ldg_stream(vs + i, pol);
-            nb[j] = ldg_stream(vs + N + i, pol);
+            na[j] = ldg_once(vs + i);
+            nb[j] = ldg_once(vs + N + i);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(us + i));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(us + N + i));
           }

@@ -349,8 +349,8 @@ shoot_cluster_kernel(const ClusterParams prm) {
         unext[i] = n0;
         unext[N + i] = n1;
         if (utraj0) { utraj0[i] = 0.f; utraj0[N + i] = 0.f; }
-        if (velout) { velout[i] = v.x; velout[N + i] = v.y; }
-        if (vtraj) { vtraj[i] = v.x; vtraj[N + i] = v.y; }
+        if (velout) { __stcs(velout + i, v.x); __stcs(velout + N + i, v.y); }      // write-only outputs: streaming stores
+        if (vtraj) { __stcs(vtraj + i, v.x); __stcs(vtraj + N + i, v.y); }
       }
       if (LOSS && s == 0) {
         // loss epilogue, regularisation term of this slab: v_0 . m0 (v_0 = vel just stored); reduced here so that no
@@ -382,7 +382,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
         const float val = gather1_ldg<BG>(src, (float)r + ucur[i], (float)c + ucur[N + i], H, W);
-        if (sd) sd[i] = val;
+        if (sd) __stcs(sd + i, val);
         if (LOSS) {
           const float d = __ldg(tarp + i) - val;
           acc_sq += d * d;
