@@ -243,6 +243,57 @@ shoot_fwd_kernel(const ShootParams prm) {
       // the (I + Du)^T stencil reads shared memory; only the 4-tap gather of m0 goes to L1/L2.
       // Band k is overwritten with m only after every thread has read it (one barrier per band); the
       // row above the next band is prefetched into a register before it is overwritten.
+#ifndef B2_EPI_PREFETCH
+#define B2_EPI_PREFETCH 1     // 3.231 -> 3.207 ms at configs[1] (both options: 3.160)
+#endif
+#if B2_EPI_PREFETCH
+      // the epilogue touches the target-frame mask and the source image for the first time: pull them into L2 one
+      // EPDiff step ahead (one 128-byte line per thread)
+      if (s == S - 1 && !hand_out) {
+        if (a.S || LOSS) {
+          const float* tp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N : a.tar + (size_t)p * N;
+          for (int i = tid * 32; i < N; i += NT * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + i));
+        }
+        if (a.sdef || LOSS) {
+          const float* sp = a.src_per_pair
+                                ? (a.src_slice_stride ? a.src + (size_t)b * a.src_slice_stride + (size_t)t * N : a.src + (size_t)p * N)
+                                : a.src + (size_t)b * (a.src_slice_stride ? a.src_slice_stride : N);
+          for (int i = tid * 32; i < N; i += NT * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + i));
+        }
+      }
+#endif
+#ifndef B2_ADSTAR_ROWS
+#define B2_ADSTAR_ROWS 1      // 3.231 -> 3.187 ms at configs[1]
+#endif
+#if B2_ADSTAR_ROWS
+      if (s > 0) {
+        // Row-sliding form of the Ad* phase: a thread owns NB CONSECUTIVE rows of its column, so u_s(r-1), u_s(r),
+        // u_s(r+1) slide through registers - three shared-memory reads per pixel (below, left, right) instead of five.
+        // The whole image is read before anything is overwritten (one barrier).  Same arithmetic: bit-identical.
+        const int rb0 = br * NB;
+        float2 m[NB];
+        float2 up = z[max(rb0 - 1, 0) * LD + c], ce = z[rb0 * LD + c];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int r = rb0 + j;
+          const float2 dn = (r == H - 1) ? ce : z[(r + 1) * LD + c];
+          const float2 lf = z[r * LD + cl];
+          const float2 rt = z[r * LD + cr];
+          const float sr = (r == 0 || r == H - 1) ? 1.f : 0.5f;
+          const float d00 = sr * (dn.x - up.x), d10 = sr * (dn.y - up.y);
+          const float d01 = sc * (rt.x - lf.x), d11 = sc * (rt.y - lf.y);
+          float w0, w1;
+          gather2<BG, kFastGather>(m0g, N, (float)r + ce.x, (float)c + ce.y, H, W, w0, w1);
+          m[j] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+          up = ce;
+          ce = dn;
+        }
+        __syncthreads();                         // every thread has read the whole image
+#pragma unroll
+        for (int j = 0; j < NB; ++j) z[(rb0 + j) * LD + c] = m[j];
+        __syncthreads();
+      }
+#else
       if (s > 0) {
 #ifndef B2_ADSTAR_G
 #define B2_ADSTAR_G 16
@@ -275,6 +326,7 @@ shoot_fwd_kernel(const ShootParams prm) {
         }
         __syncthreads();
       }
+#endif
       // ---- v = sharp(m)  (in shared memory)
       fluid_smem<H, W, true, NT>(z, twH, twW, csH, csW, fp, tid);
 

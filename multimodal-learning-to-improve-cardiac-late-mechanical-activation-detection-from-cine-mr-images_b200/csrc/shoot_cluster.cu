@@ -314,6 +314,33 @@ shoot_cluster_kernel(const ClusterParams prm) {
         // m = Ad*_{u_s} m0 on the slab; u_s and m0 come from the per-pair L2 scratch (neighbour slabs included)
         const float* u0 = ucur;
         const float* u1 = ucur + N;
+#ifndef B2_CLUSTER_ADSTAR_ROWS
+#define B2_CLUSTER_ADSTAR_ROWS 0      // measured neutral at 256x256 (11.17 vs 11.14 ms per 784-pair shard): off
+#endif
+#if B2_CLUSTER_ADSTAR_ROWS
+        // a thread walks NBc CONSECUTIVE rows of its column: u_s(r-1), u_s(r), u_s(r+1) slide through registers - six
+        // loads per pixel (row below, left, right; both planes) instead of ten.  Same values, same arithmetic.
+        {
+          int clo, chi; float sc;
+          diff_idx(c, W, clo, chi, sc);
+          const int rfirst = r0 + br * NBc;
+          float ua_up = u0[max(rfirst - 1, 0) * W + c], ub_up = u1[max(rfirst - 1, 0) * W + c];
+          float ua_c = u0[rfirst * W + c], ub_c = u1[rfirst * W + c];
+#pragma unroll 2
+          for (int k = 0; k < NBc; ++k) {
+            const int lr = br * NBc + k, r = r0 + lr;
+            const int rd = min(r + 1, H - 1);
+            const float sr = diff_scale(r, H);
+            const float ua_dn = u0[rd * W + c], ub_dn = u1[rd * W + c];
+            const float d00 = sr * (ua_dn - ua_up), d10 = sr * (ub_dn - ub_up);
+            const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]), d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+            float w0, w1;
+            gather2<BG, false>(m0r, N, (float)r + ua_c, (float)c + ub_c, H, W, w0, w1);
+            z[lr * kLDR + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
+            ua_up = ua_c; ub_up = ub_c; ua_c = ua_dn; ub_c = ub_dn;
+          }
+        }
+#else
 #pragma unroll 2
         for (int k = 0; k < NBc; ++k) {
           const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
@@ -326,6 +353,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
           gather2<BG, false>(m0r, N, (float)r + u0[i], (float)c + u1[i], H, W, w0, w1);
           z[lr * kLDR + c] = make_float2(w0 + (d00 * w0 + d10 * w1), w1 + (d01 * w0 + d11 * w1));
         }
+#endif
         __syncthreads();
       }
       float* unext = (s + 1 == S) ? uout : ((s & 1) ? ubuf1 : ubuf0);
@@ -622,6 +650,14 @@ shoot_cluster_bwd_kernel(const ShootBwdParams prm, const int64_t cluster_stride)
         // g_1 w_1) in place of g in the slab (column neighbours never leave the slab), (g_0 w_0, g_0 w_1) in the
         // scratch field Qb (row neighbours cross slab boundaries: L2) - pass B adds their transposed differences.
         SplatCarry cy{-1, 0.f, 0.f};
+#ifndef B2_CLUSTER_BWD_ROWWIN
+#define B2_CLUSTER_BWD_ROWWIN 1   // u_s rows and row-neighbour products slide through registers (as in shoot_bwd_kernel)
+#endif
+#if B2_CLUSTER_BWD_ROWWIN
+        const int rfirst = r0 + lrbase;
+        float ua_up = __ldg(us + max(rfirst - 1, 0) * W + c), ub_up = __ldg(us + N + max(rfirst - 1, 0) * W + c);
+        float ua_c = __ldg(us + rfirst * W + c), ub_c = __ldg(us + N + rfirst * W + c);
+#endif
 #pragma unroll 2
         for (int k = 0; k < NBc; ++k) {
           const int lr = lrbase + k, r = r0 + lr, i = r * W + c;
@@ -629,12 +665,21 @@ shoot_cluster_bwd_kernel(const ShootBwdParams prm, const int64_t cluster_stride)
           const int ru = max(r - 1, 0), rd = min(r + 1, H - 1);
           const int oup = ru * W + c, odn = rd * W + c, olf = r * W + cl, ort = r * W + cr;
           const float sr = diff_scale(r, H);
+#if B2_CLUSTER_BWD_ROWWIN
+          const float ua_dn = __ldg(us + odn), ub_dn = __ldg(us + N + odn);
+          const float d00 = sr * (ua_dn - ua_up), d10 = sr * (ub_dn - ub_up);
+          const float uc0 = ua_c, uc1 = ub_c;
+          ua_up = ua_c; ub_up = ub_c; ua_c = ua_dn; ub_c = ub_dn;
+          (void)oup;
+#else
           const float d00 = sr * (__ldg(us + odn) - __ldg(us + oup)), d10 = sr * (__ldg(us + N + odn) - __ldg(us + N + oup));
+          const float uc0 = __ldg(us + i), uc1 = __ldg(us + N + i);
+#endif
           const float d01 = sc * (__ldg(us + ort) - __ldg(us + olf)), d11 = sc * (__ldg(us + N + ort) - __ldg(us + N + olf));
           const float2 g = z[lr * kLDR + c];
           const float gw0 = g.x + (d00 * g.x + d01 * g.y);
           const float gw1 = g.y + (d10 * g.x + d11 * g.y);
-          const Taps t = make_taps<BG>((float)r + __ldg(us + i), (float)c + __ldg(us + N + i), H, W);
+          const Taps t = make_taps<BG>((float)r + uc0, (float)c + uc1, H, W);
           splat2_agg<BG>(A, N, t, gw0, gw1, cy, lane);
           float w0, w1, o0, o1;
           {
@@ -662,6 +707,10 @@ shoot_cluster_bwd_kernel(const ShootBwdParams prm, const int64_t cluster_stride)
         }
         splat_flush(A, N, cy);
         cluster.sync();                          // row-neighbour products of the adjacent slabs are visible
+#if B2_CLUSTER_BWD_ROWWIN
+        float qa_up = __ldcg(Qb + max(rfirst - 1, 0) * W + c), qb_up = __ldcg(Qb + N + max(rfirst - 1, 0) * W + c);
+        float qa_c = __ldcg(Qb + rfirst * W + c), qb_c = __ldcg(Qb + N + rfirst * W + c);
+#endif
 #pragma unroll 2
         for (int k = 0; k < NBc; ++k) {
           const int lr = lrbase + k, r = r0 + lr, i = r * W + c;
@@ -671,9 +720,18 @@ shoot_cluster_bwd_kernel(const ShootBwdParams prm, const int64_t cluster_stride)
           const float cmr = (r >= 1) ? diff_scale(r - 1, H) : 0.f, cpr = (r <= H - 2) ? diff_scale(r + 1, H) : 0.f;
           const float c0r = (r == H - 1 ? 1.f : 0.f) - (r == 0 ? 1.f : 0.f);
           const float2 ql = z[lr * kLDR + cl], qr = z[lr * kLDR + cr];
+#if B2_CLUSTER_BWD_ROWWIN
+          const float qa_dn = __ldcg(Qb + odn), qb_dn = __ldcg(Qb + N + odn);
+          float o0 = (cmr * qa_up - cpr * qa_dn) + (cmc * ql.x - cpc * qr.x);
+          float o1 = (cmr * qb_up - cpr * qb_dn) + (cmc * ql.y - cpc * qr.y);
+          if (c0r != 0.f) { o0 += c0r * qa_c; o1 += c0r * qb_c; }
+          qa_up = qa_c; qb_up = qb_c; qa_c = qa_dn; qb_c = qb_dn;
+          (void)oup;
+#else
           float o0 = (cmr * __ldcg(Qb + oup) - cpr * __ldcg(Qb + odn)) + (cmc * ql.x - cpc * qr.x);
           float o1 = (cmr * __ldcg(Qb + N + oup) - cpr * __ldcg(Qb + N + odn)) + (cmc * ql.y - cpc * qr.y);
           if (c0r != 0.f) { o0 += c0r * __ldcg(Qb + i); o1 += c0r * __ldcg(Qb + N + i); }
+#endif
           if (c0c != 0.f) { const float2 qc = z[lr * kLDR + c]; o0 += c0c * qc.x; o1 += c0c * qc.y; }
           __stcg(Gnext + i, gn0 + o0);
           __stcg(Gnext + N + i, gn1 + o1);
