@@ -424,11 +424,23 @@ shoot_fwd_kernel(const ShootParams prm) {
       const SectorFrame sf = sector_frame_of(a.table, a.table_slice_stride, a.theta0, a.clockwise, b);
       for (int i = tid; i < 2 * n_sectors; i += NT) tab_s[i] = sf.table[i];      // this slice's (rotated) boundaries
       for (int i = tid; i < n_sectors; i += NT) { sums_s[i] = 0ull; cnts_s[i] = 0; }
-      __syncthreads();
+#ifndef B2_STRAIN_COMPACT
+#define B2_STRAIN_COMPACT 1
+#endif
+      int* n_members = reinterpret_cast<int*>(red_s);         // free here: the loss reductions are done
+      if (tid == 0) *n_members = 0;
+      __syncthreads();                                        // also: every thread is done with z (warp phase)
       const float* tarp = a.tar_slice_stride ? a.tar + (size_t)b * a.tar_slice_stride + (size_t)t * N
                                              : a.tar + (size_t)p * N;
+#if B2_STRAIN_COMPACT
+      // z is dead from here to the next pair: it holds the list of member pixels
+      strain_bin_frame_compact<NT>(ucur, ucur + N, tarp, reinterpret_cast<const long long*>(a.moments) + 3 * b,
+                                   tab_s, n_sectors, H, W, sums_s, cnts_s, tid, sf.theta0, sf.flip,
+                                   reinterpret_cast<unsigned short*>(z), n_members);
+#else
       strain_bin_frame<NT>(ucur, ucur + N, tarp, reinterpret_cast<const long long*>(a.moments) + 3 * b,
                            tab_s, n_sectors, H, W, sums_s, cnts_s, tid, sf.theta0, sf.flip);
+#endif
       strain_store_column<NT>(sums_s, cnts_s, a.S, a.counts, (int)b, t, (int)a.T1, n_sectors, a.n_frames, tid);
     }
     __syncthreads();   // z and bins free for the next pair

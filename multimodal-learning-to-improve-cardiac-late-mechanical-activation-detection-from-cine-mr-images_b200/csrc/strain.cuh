@@ -52,6 +52,52 @@ __device__ __forceinline__ void strain_bin_frame(const float* u0, const float* u
   __syncthreads();
 }
 
+// Same accumulation with the member pixels COMPACTED first (fused forward kernel): the myocardium is ~15 % of the
+// image, so in the plain loop most warps carry a few member lanes through the whole classify / stencil / strain path.
+// Pass 1 collects the member pixel indices (ballot + one shared-memory counter bump per warp) into `list` (N entries of
+// shared memory, 16-bit: N <= 65536), pass 2 runs the heavy path on dense warps.  The sums are integer, so the order
+// the list happens to have does not change a bit of the result.  `n_s` must be zero and visible on entry.
+template <int NT>
+__device__ __forceinline__ void strain_bin_frame_compact(const float* u0, const float* u1, const float* __restrict__ mask,
+                                                         const long long* mom, const int32_t* tab_s, int n_sectors,
+                                                         int H, int W, unsigned long long* sums_s, int* cnts_s, int tid,
+                                                         float theta0, bool flip, unsigned short* list, int* n_s) {
+  const int N = H * W, lane = tid & 31;
+  for (int x = tid; x < N; x += NT) {            // N % NT == 0: whole warps iterate together
+    const bool mem = mask[x] > 0.5f;
+    const unsigned bal = __ballot_sync(0xffffffffu, mem);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(n_s, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (mem) list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)x;
+    }
+  }
+  __syncthreads();
+  const int n = *n_s;
+  const long long cnt = mom[0], sx = mom[1], sy = mom[2];
+  float c0, c1;
+  centroid_from_moments(mom, H, W, c0, c1);
+  for (int i = tid; i < n; i += NT) {
+    const int x = list[i];
+    const int r = x / W, c = x - r * W;
+    const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors, theta0, flip);
+    if (k < 0) continue;
+    int rlo, rhi, clo, chi; float sr, sc;
+    diff_idx(r, H, rlo, rhi, sr);
+    diff_idx(c, W, clo, chi, sc);
+    const float d00 = sr * (u0[rhi * W + c] - u0[rlo * W + c]);
+    const float d10 = sr * (u1[rhi * W + c] - u1[rlo * W + c]);
+    const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]);
+    const float d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+    EccTerms e; float ecc;
+    if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[x], (float)c + u1[x], c0, c1, e, ecc)) continue;
+    atomicAdd(&sums_s[k], ecc_to_fixed(ecc));
+    atomicAdd(&cnts_s[k], 1);
+  }
+  __syncthreads();
+}
+
 // ---- adjoint of the reduction (shared by strain_sector_bwd_kernel and the prologue of the fused EPDiff adjoint)
 // dL/dEcc of a member pixel of sector k of pair (b, t): (gS[b,k,t] + the edge-padded columns of the last frame) / count
 template <int NT>
