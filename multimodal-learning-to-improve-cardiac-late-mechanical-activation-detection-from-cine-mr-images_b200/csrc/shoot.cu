@@ -709,8 +709,12 @@ shoot_bwd_kernel(const ShootBwdParams prm) {
         for (int i = tid; i < 2 * sd.n_sectors; i += NT) tab_s[i] = sf.table[i];
         strain_bwd_weights<NT>(sd.gS, sd.counts, (int)b, t, (int)sd.T1, sd.n_sectors, sd.n_frames, gk_s, tid);
         __syncthreads();            // accumulator seeded, table and weights visible
+#ifndef B2_BWD_SEED_COMPACT
+#define B2_BWD_SEED_COMPACT 1
+#endif
+        // the field buffer z is not in use before the first compose adjoint: it holds the list of member pixels
         strain_bwd_frame<NT>(uS, uS + N, tarp, sd.moments + 3 * b, tab_s, sd.n_sectors, H, W, gk_s, Gcur, Gcur + N, tid,
-                             sf.theta0, sf.flip);
+                             sf.theta0, sf.flip, B2_BWD_SEED_COMPACT ? reinterpret_cast<unsigned short*>(z) : nullptr);
       }
       if (sd.g_sq) {
         const float* srcp = sd.src_per_pair

@@ -440,6 +440,44 @@ shoot_cluster_kernel(const ClusterParams prm) {
                                              : a.tar + (size_t)p * N;
       const float* u0 = ucur;
       const float* u1 = ucur + N;
+#ifndef B2_CLUSTER_STRAIN_COMPACT
+#define B2_CLUSTER_STRAIN_COMPACT 1
+#endif
+#if B2_CLUSTER_STRAIN_COMPACT
+      // member pixels of the slab compacted first (as in shoot_fwd_kernel: strain_bin_frame_compact): the slab buffer z
+      // is dead after the last compose and holds the list of slab-local pixel indices (64 x 256 = 16 bits)
+      unsigned short* list = reinterpret_cast<unsigned short*>(z);
+      __shared__ int n_mem_s;
+      if (tid == 0) n_mem_s = 0;
+      __syncthreads();
+      for (int k = 0; k < NBc; ++k) {
+        const int lr = k * RBc + br;
+        const bool mem = tarp[(r0 + lr) * W + c] > 0.5f;
+        const unsigned bal = __ballot_sync(0xffffffffu, mem);
+        if (bal) {
+          int base = 0;
+          if ((tid & 31) == 0) base = atomicAdd(&n_mem_s, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (mem) list[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)(lr * W + c);
+        }
+      }
+      __syncthreads();
+      const int n_mem = n_mem_s;
+      for (int j = tid; j < n_mem; j += kCNT) {
+        const int li = list[j], cm = li % W, r = r0 + li / W, i = r * W + cm;
+        const int ksec = classify_sector(cnt * r - sx, cnt * cm - sy, sf.table, ns, sf.theta0, sf.flip);
+        if (ksec < 0) continue;
+        int rlo, rhi, clo, chi; float sr, sc;
+        diff_idx(r, H, rlo, rhi, sr);
+        diff_idx(cm, W, clo, chi, sc);
+        const float d00 = sr * (u0[rhi * W + cm] - u0[rlo * W + cm]), d10 = sr * (u1[rhi * W + cm] - u1[rlo * W + cm]);
+        const float d01 = sc * (u0[r * W + chi] - u0[r * W + clo]), d11 = sc * (u1[r * W + chi] - u1[r * W + clo]);
+        EccTerms e; float ecc;
+        if (!ecc_eval(d00, d01, d10, d11, (float)r + u0[i], (float)cm + u1[i], c0, c1, e, ecc)) continue;
+        atomicAdd(bins + ksec, ecc_to_fixed(ecc));
+        atomicAdd(cnts + ksec, 1u);
+      }
+#else
       for (int k = 0; k < NBc; ++k) {
         const int lr = k * RBc + br, r = r0 + lr, i = r * W + c;
         if (!(tarp[i] > 0.5f)) continue;
@@ -455,6 +493,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
         atomicAdd(bins + ksec, ecc_to_fixed(ecc));
         atomicAdd(cnts + ksec, 1u);
       }
+#endif
       cluster.sync();   // release/acquire at cluster scope: global writes of the other CTAs are visible
       if (rk == 0) {
         for (int k = tid; k < ns; k += kCNT) {

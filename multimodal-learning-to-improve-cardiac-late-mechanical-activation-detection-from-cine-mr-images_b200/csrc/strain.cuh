@@ -115,16 +115,39 @@ __device__ __forceinline__ void strain_bwd_weights(const float* __restrict__ gS,
 
 // Accumulates dL/du of one pair into d0 / d1 with float atomics (d zero- or seed-filled by the caller, complete
 // before the call; gk_s and tab_s visible to the CTA).  All threads of the CTA call this.
+// `list` (optional): N 16-bit entries of shared memory that are free during the call - the member pixels are then
+// compacted first and the heavy path runs on dense warps (see strain_bin_frame_compact); N % NT == 0, N <= 65536.
 template <int NT>
 __device__ __forceinline__ void strain_bwd_frame(const float* u0, const float* u1, const float* __restrict__ mask,
                                                  const long long* mom, const int32_t* tab_s, int n_sectors, int H, int W,
-                                                 const float* gk_s, float* d0, float* d1, int tid, float theta0, bool flip) {
+                                                 const float* gk_s, float* d0, float* d1, int tid, float theta0, bool flip,
+                                                 unsigned short* list = nullptr) {
   const long long cnt = mom[0], sx = mom[1], sy = mom[2];
   float c0, c1;
   centroid_from_moments(mom, H, W, c0, c1);
   const int N = H * W;
-  for (int x = tid; x < N; x += NT) {
-    if (!(mask[x] > 0.5f)) continue;
+  __shared__ int n_members_s;
+  int n_items = N;
+  if (list) {
+    if (tid == 0) n_members_s = 0;
+    __syncthreads();
+    const int lane = tid & 31;
+    for (int x = tid; x < N; x += NT) {
+      const bool mem = mask[x] > 0.5f;
+      const unsigned bal = __ballot_sync(0xffffffffu, mem);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&n_members_s, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (mem) list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)x;
+      }
+    }
+    __syncthreads();
+    n_items = n_members_s;
+  }
+  for (int it = tid; it < n_items; it += NT) {
+    const int x = list ? (int)list[it] : it;
+    if (!list && !(mask[x] > 0.5f)) continue;
     const int r = x / W, c = x - r * W;
     const int k = classify_sector(cnt * r - sx, cnt * c - sy, tab_s, n_sectors, theta0, flip);
     if (k < 0) continue;
