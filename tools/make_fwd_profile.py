@@ -99,6 +99,15 @@ whole pairs first, then the last 148 pairs in chunks of two EPDiff steps that an
 (u_s, m0) in the scratch (flag + fence hand-over, DESIGN.md section 4) - the kernel ends within one chunk of perfect
 balance instead of one pair (3.42 -> 3.28 ms).  Last, the radix-2 butterflies with non-trivial twiddles never form the
 product: `x0 = e + w o` as chained FMAs, `x1 = 2 e - x0` (6 instead of 8 instructions, `bfly16` in `fft.cuh`): 3.274 -> 3.245 ms.
+End of round 2 (3.232 -> 3.129 ms): the capture before these steps showed the L1 / shared-memory data pipe as the busiest
+unit (72 % of its wavefront peak) next to 63 % of the issue slots, so (1) the `Ad*` phase now walks CONSECUTIVE rows per
+thread with `u_s(r-1), u_s(r), u_s(r+1)` sliding through registers - three shared-memory reads per pixel instead of five
+(433 M -> 402 M shared wavefronts, -1.4 %); (2) the target mask and the source image of the epilogue are prefetched into L2
+one EPDiff step ahead (first touch, HBM latency: -0.8 %); (3) the strain epilogue compacts the member pixels (the
+myocardium is ~15 % of the image) with a ballot + one shared counter bump per warp into the dead field buffer and runs the
+classify / stencil / strain path on dense warps (-1.0 %).  Measured and rejected in the same series (DESIGN.md section 6):
+packed `FADD2 / FFMA2` arithmetic, a tabulated Fourier multiplier, twiddle power tables read with 16-byte broadcast loads,
+L2 prefetch of the next pair's `v0` with a ticket drawn one step ahead.
 
 Per-source-line roll-up (`tools/ncu_lines.py`; share of stall samples / of executed warp instructions, dominant stalls):
 
@@ -106,7 +115,7 @@ Per-source-line roll-up (`tools/ncu_lines.py`; share of stall samples / of execu
 {lines}
 ```
 
-Reading: still issue-bound (two thirds of the issue slots, DRAM 5 %, L2 11 %).  `fft.cuh` is 49 % of the instructions (radix
+Reading: issue slots and the L1 / shared-memory data pipe are the two busy units (two thirds each; DRAM 5 %, L2 11 %).  `fft.cuh` is 49 % of the instructions (radix
 butterflies with compile-time twiddles; 7 shared-memory round trips per operator are left and each of them sits between
 two transposing passes, i.e. cannot be fused in registers), the two bilinear gathers (`common.cuh`) 31 %.  Barrier
 stalls rose from 8 % to 13 % of the samples: the fused middle is the longest uninterrupted phase, so arrival times at
