@@ -315,6 +315,9 @@ int b2_regroup_pairs_bwd(const float* gout, const int32_t* pair_slot, float* gu,
  * b2_unpack_u8 widens on the device: out[i] = (float)in[i]; n multiple of 4, in 4-byte / out 16-byte aligned. */
 int b2_pack_binary_u8_host(const float* src_host, uint8_t* dst_host, int64_t n, int threads);
 int b2_unpack_u8(const uint8_t* in, float* out, int64_t n, void* stream);
+/* The same masks as ONE BIT per pixel (a dataset that stores numpy.packbits(mask, axis=-1): most significant bit
+ * first): out[i] = (float)bit i of in; n pixels, multiple of 8, out 16-byte aligned. */
+int b2_unpack_bits(const uint8_t* in, float* out, int64_t n, void* stream);
 
 /* Device properties the host side needs for grid sizing / reporting. */
 int b2_device_sm_count(int device);

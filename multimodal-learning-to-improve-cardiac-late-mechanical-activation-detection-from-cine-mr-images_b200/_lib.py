@@ -115,6 +115,7 @@ SIGNATURES = {
     "b2_regroup_pairs_bwd": (c_int, [c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f]),
     "b2_pack_binary_u8_host": (c_int, [c_f, c_f, c_i64, c_int]),
     "b2_unpack_u8": (c_int, [c_f, c_f, c_i64, c_f]),
+    "b2_unpack_bits": (c_int, [c_f, c_f, c_i64, c_f]),
     "b2_device_sm_count": (c_int, [c_int]),
     "b2_shoot_cluster_occupancy": (c_int, [c_f, c_f]),
 }

@@ -30,6 +30,18 @@ unpack_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_
   }
 }
 
+// One bit per pixel (numpy.packbits order: pixel j of a row sits in byte j / 8 at bit 7 - j % 8).  A thread widens the
+// four pixels of one nibble into one 128-bit store; the two threads that share a byte read it through L1.
+__global__ void __launch_bounds__(kUnpackThreads)
+unpack_bits_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n4) {
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (int64_t i = (int64_t)blockIdx.x * kUnpackThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kUnpackThreads) {
+    const unsigned b = __ldg(in + (i >> 1));
+    const unsigned nib = (i & 1) ? (b & 15u) : (b >> 4);
+    out4[i] = make_float4((float)((nib >> 3) & 1u), (float)((nib >> 2) & 1u), (float)((nib >> 1) & 1u), (float)(nib & 1u));
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -156,6 +168,20 @@ extern "C" int b2_unpack_u8(const uint8_t* in, float* out, int64_t n, void* stre
   int64_t blocks = (n4 + kUnpackThreads - 1) / kUnpackThreads;
   if (blocks > 148 * 8) blocks = 148 * 8;
   unpack_u8_kernel<<<(unsigned)blocks, kUnpackThreads, 0, (cudaStream_t)stream>>>(in, out, n4);
+  B2_CHECK_LAUNCH();
+  return B2_OK;
+}
+
+// Device: out[i] = bit i of the numpy.packbits stream `in` (most significant bit first), i < n.  n must be a multiple
+// of 8 (whole bytes) and out 16-byte aligned.
+extern "C" int b2_unpack_bits(const uint8_t* in, float* out, int64_t n, void* stream) {
+  if (!in || !out) return B2_E_NULL;
+  if (n <= 0 || (n & 7)) return B2_E_SHAPE;
+  if (reinterpret_cast<uintptr_t>(out) & 15) return B2_E_PARAM;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + kUnpackThreads - 1) / kUnpackThreads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  unpack_bits_kernel<<<(unsigned)blocks, kUnpackThreads, 0, (cudaStream_t)stream>>>(in, out, n4);
   B2_CHECK_LAUNCH();
   return B2_OK;
 }

@@ -490,13 +490,16 @@ class HostPipeline:
     ``float32``.  For fp32 volumes ``pack_masks=True`` narrows each chunk on the host (multi-threaded, verified to
     be exactly 0/1, otherwise that chunk is copied as fp32) while the ``v0`` copy of the same chunk occupies the bus;
     whether that pays is MEASURED: the pass is timed against the copy it has to hide behind and switched off for
-    later calls when it does not fit (few or busy host cores).  Results are bit-identical on every route.
+    later calls when it does not fit (few or busy host cores).  A dataset that stores its masks as ONE BIT per pixel
+    hands over ``numpy.packbits(mask, axis=-1)``: ``uint8`` of shape (B,1,T,H,W/8), most significant bit first
+    (W a multiple of 8), widened on the device by ``b2_unpack_bits`` - no host pass, an eighth of the bytes of the
+    ``uint8`` route.  Results are bit-identical on every route.
     ``self.h2d_bytes`` is the number of bytes the last call copied to the device.
     """
 
     def __init__(self, B, T, H, W, metric: FluidMetric, num_steps=10, T_end=1.0, n_sectors=N_SECTORS, n_frames=40,
                  chunk_slices=None, device=None, background="clamp", pack_masks=True, pack_threads=0, theta0=None,
-                 clockwise=None):
+                 clockwise=None, n_stages=3):
         self.dev = torch.device(device if device is not None else torch.cuda.current_device())
         if self.dev.index is None:
             self.dev = torch.device("cuda", torch.cuda.current_device())
@@ -526,7 +529,7 @@ class HostPipeline:
             # Three staging buffers: with two, the copy of chunk i+1 has to wait for the kernel of chunk i-1, which
             # ends just about when the copy of chunk i does (kernel and copy times per chunk are nearly equal) - any
             # jitter stalls the copy engine.
-            self.n_stages = 3
+            self.n_stages = max(2, int(n_stages))
             self._next_stage = 0
             self.stage = [{"vol": torch.empty((cs, 1, T, H, W), device=dev),
                            "v0": torch.empty((cs * T1, 2, H, W), device=dev),
@@ -554,15 +557,18 @@ class HostPipeline:
 
     def submit(self, v0_host: torch.Tensor, vol_host: torch.Tensor) -> PipelineResult:
         B, T, T1, H, W, cs = self.B, self.T, self.T1, self.H, self.W, self.chunk
-        if tuple(vol_host.shape) != (B, 1, T, H, W) or tuple(v0_host.shape) != (B * T1, 2, H, W):
+        bit_masks = (vol_host.dtype == torch.uint8 and W % 8 == 0 and W > 8
+                     and tuple(vol_host.shape) == (B, 1, T, H, W // 8))
+        if not (bit_masks or tuple(vol_host.shape) == (B, 1, T, H, W)) or tuple(v0_host.shape) != (B * T1, 2, H, W):
             raise _lib.B2Error(f"shape mismatch: v0 {tuple(v0_host.shape)}, vol {tuple(vol_host.shape)}")
         if vol_host.dtype == torch.bool:
             vol_host = vol_host.view(torch.uint8)
-        byte_masks = vol_host.dtype == torch.uint8
+        byte_masks = vol_host.dtype == torch.uint8 and not bit_masks
         if not (v0_host.is_contiguous() and vol_host.is_contiguous() and v0_host.dtype == torch.float32
-                and (byte_masks or vol_host.dtype == torch.float32)) or v0_host.is_cuda or vol_host.is_cuda:
-            raise _lib.B2Error("HostPipeline expects contiguous host tensors: fp32 v0, fp32 / uint8 / bool masks")
-        if byte_masks and not self.byte_masks_ok:
+                and (byte_masks or bit_masks or vol_host.dtype == torch.float32)) or v0_host.is_cuda or vol_host.is_cuda:
+            raise _lib.B2Error("HostPipeline expects contiguous host tensors: fp32 v0, fp32 / uint8 / bool / "
+                               "bit-packed masks")
+        if (byte_masks or bit_masks) and not self.byte_masks_ok:
             raise _lib.B2Error("uint8 masks need T*H*W to be a multiple of 4")
         self.h2d_bytes = 0
         with torch.cuda.device(self.dev), torch.no_grad():
@@ -582,11 +588,19 @@ class HostPipeline:
                     self.h2d_bytes += nb * T1 * 2 * H * W * 4
                     n = nb * T * H * W
                     src_u8 = None
-                    if byte_masks:
+                    if bit_masks:
+                        st["vol_u8"][: n // 8].copy_(vol_host[b0:b1].reshape(-1), non_blocking=True)
+                        check(lib().b2_unpack_bits(ptr(st["vol_u8"]), ptr(st["vol"]), n,
+                                                   C.c_void_p(self.copy_stream.cuda_stream)), "b2_unpack_bits")
+                        _lib.count_launch()
+                        self.h2d_bytes += n // 8
+                    elif byte_masks:
                         src_u8 = vol_host[b0:b1].reshape(-1)
                     elif self.pack_masks:
                         src_u8 = self._narrow_on_host(st, vol_host[b0:b1], n, nb * T1 * 2 * H * W * 4)
-                    if src_u8 is not None:
+                    if bit_masks:
+                        pass
+                    elif src_u8 is not None:
                         st["vol_u8"][:n].copy_(src_u8[:n], non_blocking=True)
                         check(lib().b2_unpack_u8(ptr(st["vol_u8"]), ptr(st["vol"]), n,
                                                  C.c_void_p(self.copy_stream.cuda_stream)), "b2_unpack_u8")

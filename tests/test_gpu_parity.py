@@ -1197,6 +1197,28 @@ def test_host_pipeline_returns_complete_result_and_takes_byte_masks(pkg, dev):
     assert torch.equal(r1.get(), ref) and torch.equal(r2.get(), ref)
     with pytest.raises(RuntimeError):
         pipe(v0, vol.to(torch.int32))
+    # one bit per pixel: numpy.packbits along the row (most significant bit first), widened by b2_unpack_bits
+    bits = torch.from_numpy(np.packbits(vol.numpy() > 0.5, axis=-1)).pin_memory()
+    assert tuple(bits.shape) == (B, 1, T, H, W // 8)
+    assert torch.equal(pipe(v0, bits), ref)
+    assert pipe.h2d_bytes == n_v0 + vol.numel() // 8
+    r1, r2 = pipe.submit(v0, bits), pipe.submit(v0, u8)
+    assert torch.equal(r1.get(), ref) and torch.equal(r2.get(), ref)
+
+
+def test_unpack_bits_matches_numpy(pkg, dev):
+    """b2_unpack_bits == numpy.unpackbits (bit order 'big'), ragged tail sizes, and its argument checks."""
+    L = pkg._lib
+    rng = np.random.default_rng(21)
+    for n in (8, 40, 4096, 128 * 128 * 25 + 8):
+        packed = rng.integers(0, 256, n // 8, dtype=np.uint8)
+        want = torch.from_numpy(np.unpackbits(packed).astype(np.float32))
+        src = torch.from_numpy(packed).to(dev)
+        out = torch.full((n + 4,), -7.0, device=dev)
+        assert L.lib().b2_unpack_bits(L.ptr(src), L.ptr(out), n, L.stream(dev)) == 0
+        assert torch.equal(out[:n].cpu(), want) and bool((out[n:] == -7.0).all())
+    assert L.lib().b2_unpack_bits(L.ptr(src), L.ptr(out), 12, L.stream(dev)) != 0
+    assert L.lib().b2_unpack_bits(None, L.ptr(out), 8, L.stream(dev)) != 0
 
 
 def test_regroup_is_differentiable(pkg, oracle, dev):
