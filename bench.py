@@ -391,9 +391,27 @@ def main():
     def kernel_only():
         pkg._lib.check(lib.b2_shoot_fwd(ctypes.byref(a), ptr(ws), nws, stream()), "b2_shoot_fwd")
 
-    ms_kernel, _ = timed(kernel_only, args.steps, 3)
+    def timed_launches(fn, steps, warmup):
+        # average duration of the individual launches: one event pair around EACH launch on the launching stream, so
+        # that a descheduled host thread between two launches (seen once: +2.8 % on the 20-launch region) is not
+        # booked as kernel time; max over ranks like every other number
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a0, a1 in ev:
+            a0.record()
+            fn()
+            a1.record()
+        barrier()
+        per = sorted(a0.elapsed_time(a1) for a0, a1 in ev)
+        t = torch.tensor([sum(per) / len(per)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), per[0], per[-1]
+
+    k_ms, k_min, k_max = timed_launches(kernel_only, args.steps, 3)
     peak, peak_src = peaks()
-    k_ms = ms_kernel / args.steps
     achieved = P * BYTES_PER_PAIR / (k_ms * 1e-3) / 1e9
     del out, ws, tar_flat, counts, pipe
     torch.cuda.empty_cache()
@@ -442,6 +460,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "shoot_fwd_kernel<128,128,1024,clamp> (fused flat + 10 EPDiff steps + warp + strain)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": measured_traffic(), "peak_source": peak_src, "kernel_ms": k_ms,
+                             "kernel_ms_min_max": [k_min, k_max], "launches_timed": args.steps,
                              "algorithmic_bytes_per_launch": P * BYTES_PER_PAIR,
                              "note": "op-level algorithmic bytes (700*N per pair); the fused kernel keeps m/v on chip, "
                                      "so real DRAM traffic is far lower (see profiles/); traffic is null when the kernel "
