@@ -88,7 +88,7 @@ Launch list of the timed region (`r02_launches.csv`; cold-cache, serialised):
 {ll}
 
 (`shoot_fwd_kernel` dominates the process; the cutlass sgemm launches are the 1 s clock spin-up outside the timed region;
-`unpack_u8_kernel` and `mask_moments_kernel` belong to the host-buffer pipeline and the resident step.)
+`unpack_bits_kernel` and `mask_moments_kernel` belong to the host-buffer pipeline and the resident step.)
 
 What changed against round 1: the second radix pass of the forward column FFT, the symbol multiply and the first radix pass
 of the inverse column FFT run in registers on mirror-closed pairs of tasks (`fluid_cols_mid_fused`, DESIGN.md section 4):
