@@ -340,6 +340,31 @@ def test_strain_analytic_on_gpu(pkg, dev):
     assert (S[0, 0, :, 1] - (s * s - 1) / 2).abs().max() < 2e-6
 
 
+@pytest.mark.parametrize("H", [64, 128, 256])
+def test_constant_velocity_is_a_translation(pkg, dev, H):
+    """Known answer for the whole path, independent of either oracle: a spatially constant initial velocity c is a
+    fixed point of the EPDiff flow (flat / sharp scale constants, Ad* with Du = 0 changes nothing), so after S steps
+    the inverse-map displacement is u = -T c everywhere, ``velocity`` = c, the momentum is gamma c, the warped
+    source is the source shifted by the (integer) c with edge clamping, and the strain of a translation is zero.
+    Runs the fused single-CTA kernels (64, 128) and the 4-CTA cluster kernel (256) at S = 10."""
+    W, B, T, S = H, 2, 3, 10
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    shifts = torch.tensor([[2.0, -3.0], [0.0, 1.0], [-1.0, -2.0], [3.0, 0.0]])
+    v0 = shifts.view(4, 2, 1, 1).expand(4, 2, H, W).contiguous()
+    out = pkg.shoot_warp_strain(v0.to(dev), src_vol.to(dev), tar_vol.to(dev), pkg.FluidMetric(PARAMS), num_steps=S)
+    assert (out["displacement"].cpu() + v0).abs().max() < 2e-5
+    assert (out["velocity"].cpu() - v0).abs().max() < 2e-5
+    m = out["momentum"].cpu()
+    assert (m - PARAMS[2] * v0).abs().max() < 1e-6               # flat(const) = gamma * const
+    src = src_vol[:, 0, 0]                                        # frame 0 of each slice is the source of its pairs
+    r, c = torch.arange(H), torch.arange(W)
+    for p in range(4):
+        a, b = int(shifts[p, 0]), int(shifts[p, 1])
+        want = src[p // (T - 1)][(r - a).clamp(0, H - 1)][:, (c - b).clamp(0, W - 1)]
+        assert (out["deformed_source"][p // (T - 1), 0, p % (T - 1)].cpu() - want).abs().max() < 1e-4
+    assert out["strain_matrix"].abs().max() < 1e-5
+
+
 @pytest.mark.parametrize("cfg", [(3, 3, 16, 16, 3), (2, 4, 32, 32, 3), (2, 5, 64, 64, 10), (1, 3, 128, 128, 10),
                                  (1, 3, 256, 256, 2), (2, 3, 64, 128, 3), (1, 3, 128, 256, 2)])
 def test_forward_volume_parity(pkg, oracle, dev, cfg):

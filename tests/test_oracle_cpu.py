@@ -295,6 +295,30 @@ def test_c_oracle_matches_torch(oracle, pkg, cfg):
     assert np.array_equal(np.array(list(tab)).reshape(126, 2), oracle.sector_boundaries(126))
 
 
+def test_oracles_constant_velocity_is_a_translation(oracle, pkg):
+    """Known answer that pins both oracles to the mathematics instead of to each other: a constant initial velocity
+    c is a fixed point of the EPDiff flow, so u = -T c, velocity = c, momentum = gamma c, the warped source is the
+    source shifted by the integer c (edge clamp) and the strain of a translation vanishes."""
+    from oracle import c_oracle
+    B, T, H, W, S = 2, 3, 32, 32, 10
+    par = (1.0, 0.1, 0.05)
+    vol = pkg.synthetic.synthetic_masks(B, T, H, W)
+    sv, tv = oracle.split_vol_to_registration_pairs(vol, "Lagrangian", 3)
+    shifts = torch.tensor([[2.0, -3.0], [0.0, 1.0], [-1.0, -2.0], [3.0, 0.0]])
+    v0 = shifts.view(4, 2, 1, 1).expand(4, 2, H, W).contiguous()
+    r, c = torch.arange(H), torch.arange(W)
+    for out in (oracle.forward_volume(v0, sv, tv, oracle.FluidMetric(par), S),
+                c_oracle.forward_volume(v0, vol, par, S, nthreads=2)):
+        assert (out["displacement"] + v0).abs().max() < 1e-5
+        assert (out["velocity"] - v0).abs().max() < 1e-5
+        assert (out["momentum"] - par[2] * v0).abs().max() < 1e-6
+        for p in range(4):
+            a, b = int(shifts[p, 0]), int(shifts[p, 1])
+            want = vol[p // (T - 1), 0, 0][(r - a).clamp(0, H - 1)][:, (c - b).clamp(0, W - 1)]
+            assert (out["deformed_source"][p // (T - 1), 0, p % (T - 1)] - want).abs().max() < 1e-4
+        assert out["strain_matrix"].abs().max() < 1e-5
+
+
 # ----------------------------------------------------------------- augmentation (reference affine.py)
 @pytest.fixture(scope="module")
 def aug_golden():
