@@ -208,6 +208,13 @@ typedef struct b2_shoot_args {
   const int32_t* clockwise;
   int32_t flags;           /* B2_FLAG_* */
   int32_t reserved_;
+  /* Optional pair range: with pair_count > 0 only the frame-pairs [pair_begin, pair_begin + pair_count) of the B*T1
+   * pairs are processed; every pointer still addresses the whole batch and the outputs of the other pairs are left
+   * untouched (a slice may be cut anywhere: its strain-matrix columns are written per pair).  Lets two launches
+   * share one batch at pair granularity - the 256x256 cluster kernel and the op-level sequence on the SMs the
+   * clusters cannot occupy.  Supported on the 256x256 cluster path and the op-level path, without traj;
+   * B2_E_PARAM elsewhere.  0 / 0 = all pairs. */
+  int64_t pair_begin, pair_count;
 } b2_shoot_args;
 int64_t b2_sizeof_shoot_args(void);   /* ABI check for bindings that mirror the struct */
 

@@ -37,6 +37,7 @@ class ShootArgs(C.Structure):
         ("loss_terms", C.c_void_p),
         ("table_slice_stride", C.c_int64), ("theta0", C.c_void_p), ("clockwise", C.c_void_p),
         ("flags", C.c_int32), ("reserved_", C.c_int32),
+        ("pair_begin", C.c_int64), ("pair_count", C.c_int64),
     ]
 
 

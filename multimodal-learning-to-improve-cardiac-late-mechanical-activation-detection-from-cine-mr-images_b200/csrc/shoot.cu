@@ -41,6 +41,9 @@ int adstar_bwd_impl(const float* gout, const float* u, const float* m0, float* d
 int cluster_grid_clusters(int64_t P);
 int64_t cluster_workspace_bytes(int64_t P);
 int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t st);
+int strain_sector_fwd_range(const float* u, const float* tar, const int64_t* moments, const b2_sector_frame* frame,
+                            float* S, int32_t* counts, int64_t B, int64_t T1, int64_t H, int64_t W, int n_sectors,
+                            int n_frames, int64_t p0, int64_t np, cudaStream_t st);   // strain.cu
 int64_t cluster_bwd_workspace_bytes(int64_t P);
 int launch_shoot_cluster_bwd(const ShootBwdParams& prm, int background, cudaStream_t st);
 // 256x256 runs on the cluster kernels unless the caller asks for the op-level path or the device cannot
@@ -1123,6 +1126,12 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   if (need <= 0) return B2_E_FFTSIZE;
   if (!workspace || workspace_bytes < need) return B2_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  // optional pair range [p0, p0 + np) of the batch (cluster path and op-level path, inference only)
+  if (a.pair_count < 0 || a.pair_begin < 0 || (a.pair_count == 0 && a.pair_begin != 0)) return B2_E_PARAM;
+  const bool ranged = a.pair_count > 0;
+  const int64_t p0 = ranged ? a.pair_begin : 0, np = ranged ? a.pair_count : P;
+  if (p0 + np > P) return B2_E_SHAPE;
+  if (ranged && (a.traj || fused_size(H, W, a.flags))) return B2_E_PARAM;
 
   if (fused_size(H, W, a.flags)) {
     ShootParams prm;
@@ -1146,40 +1155,42 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
     return B2_E_FFTSIZE;
   }
 
-  if (cluster_size(H, W, P, a.flags)) {
+  if (cluster_size(H, W, np, a.flags)) {
     if (a.S && (a.n_sectors > kMaxSectors)) return B2_E_PARAM;
     return launch_shoot_cluster(a, workspace, st);
   }
 
-  // ---- path B: op-level sequence
+  // ---- path B: op-level sequence (on the pairs [p0, p0 + np); the per-pair tensors are addressed from pair p0)
   if (a.src_slice_stride || a.tar_slice_stride) return B2_E_PARAM;   // strided volumes: fused path only
   if (a.loss_terms && (!a.sdef || !a.vel)) return B2_E_NULL;         // the op-level reduction reads both outputs
-  if (b2_fluid_workspace_bytes(P, H, W) <= 0) return B2_E_FFTSIZE;
+  if (b2_fluid_workspace_bytes(np, H, W) <= 0) return B2_E_FFTSIZE;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   const size_t fbytes = align256(sizeof(float) * (size_t)P * field);
-  const float* m0 = a.v0;
+  const size_t off2 = (size_t)p0 * field, off1 = (size_t)p0 * H * W;  // first element of pair p0 in 2- / 1-plane tensors
+  const float* v0p = a.v0 + off2;
+  float* up = a.u + off2;
+  float* velp = a.vel ? a.vel + off2 : nullptr;
+  const float* m0 = v0p;
   if (!a.v0_is_momentum) {
-    float* m0w = a.m0 ? a.m0 : reinterpret_cast<float*>(ws);
-    if (int e = fluid_apply_impl(a.v0, m0w, P, H, W, a.alpha, a.beta, a.gamma, 0, ws + 3 * fbytes,
-                                 b2_fluid_workspace_bytes(P, H, W), st))
+    float* m0w = a.m0 ? a.m0 + off2 : reinterpret_cast<float*>(ws);
+    if (int e = fluid_apply_impl(v0p, m0w, np, H, W, a.alpha, a.beta, a.gamma, 0, ws + 3 * fbytes,
+                                 b2_fluid_workspace_bytes(np, H, W), st))
       return e;
     m0 = m0w;
   }
   float* uscr = reinterpret_cast<float*>(ws + fbytes);
-  (void)fbytes;
   void* fws = ws + 3 * fbytes;
-  const int64_t fws_bytes = b2_fluid_workspace_bytes(P, H, W);
   const int S = a.num_steps;
   const float dt = a.T / (float)S;
-  const size_t n = (size_t)P * field;
+  const size_t n = (size_t)P * field;                                // trajectory stride (never with a pair range)
   const float* ucur = nullptr;
   for (int s = 0; s < S; ++s) {
     // v_s goes to the trajectory (training), to `vel` at s = 0, or nowhere; m/v stay out of HBM otherwise
-    float* vout = a.traj ? a.traj + (size_t)(s * 2 + 1) * n : ((s == 0 && a.vel) ? a.vel : nullptr);
+    float* vout = a.traj ? a.traj + (size_t)(s * 2 + 1) * n : ((s == 0 && velp) ? velp : nullptr);
     float* unext;
-    if (a.traj) unext = (s + 1 < S) ? a.traj + (size_t)((s + 1) * 2) * n : a.u;
-    else unext = (((S - (s + 1)) & 1) == 0) ? a.u : uscr;
-    if (int e = epdiff_step_big(ucur, m0, unext, vout, fws, P, H, W, a.alpha, a.beta, a.gamma, dt, a.background, st)) return e;
+    if (a.traj) unext = (s + 1 < S) ? a.traj + (size_t)((s + 1) * 2) * n : up;
+    else unext = (((S - (s + 1)) & 1) == 0) ? up : uscr;
+    if (int e = epdiff_step_big(ucur, m0, unext, vout, fws, np, H, W, a.alpha, a.beta, a.gamma, dt, a.background, st)) return e;
     if (s == 0) {
       if (a.traj) {
         B2_CUDA(cudaMemsetAsync(a.traj, 0, sizeof(float) * n, st));
@@ -1190,19 +1201,32 @@ extern "C" int b2_shoot_fwd(const b2_shoot_args* args, void* workspace, int64_t 
   }
   if (a.sdef) {
     if (a.src_per_pair) {
-      if (int e = b2_interp_fwd(a.src, a.u, a.sdef, P, P, P, 1, H, W, 1.f, a.background, stream)) return e;
-    } else {   // one source image per slice, indexed in-kernel (no repeat)
+      if (int e = b2_interp_fwd(a.src + off1, up, a.sdef + off1, np, np, np, 1, H, W, 1.f, a.background, stream)) return e;
+    } else if (!ranged) {   // one source image per slice, indexed in-kernel (no repeat)
       if (int e = b2_warp_fwd(a.src, a.u, a.sdef, a.B, a.T1, 1, H, W, 1.f, a.background, stream)) return e;
+    } else {                // a range may cut slices: head segment, whole slices, tail segment (one source image each)
+      int64_t p = p0;
+      const int64_t pend = p0 + np;
+      while (p < pend) {
+        const int64_t b = p / a.T1, t = p % a.T1;
+        int64_t nb = 1, nt = a.T1 - t;
+        if (t == 0 && pend - p >= a.T1) { nb = (pend - p) / a.T1; nt = a.T1; }
+        else if (nt > pend - p) nt = pend - p;
+        if (int e = b2_warp_fwd(a.src + (size_t)b * H * W, a.u + (size_t)p * field, a.sdef + (size_t)p * H * W, nb, nt, 1,
+                                H, W, 1.f, a.background, stream))
+          return e;
+        p += nb * nt;
+      }
     }
   }
   if (a.S) {
     const b2_sector_frame fr{a.table, a.table_slice_stride, a.theta0, a.clockwise};
-    if (int e = b2_strain_sector_fwd_ex(a.u, a.tar, a.moments, &fr, a.S, a.counts, a.B, a.T1, H, W, a.n_sectors,
-                                        a.n_frames, stream))
+    if (int e = strain_sector_fwd_range(a.u, a.tar, a.moments, &fr, a.S, a.counts, a.B, a.T1, H, W, a.n_sectors,
+                                        a.n_frames, p0, np, st))
       return e;
   }
   if (a.loss_terms) {
-    if (int e = b2_recon_loss_terms(a.sdef, a.tar, a.vel, m0, a.loss_terms, P, H, W, stream)) return e;
+    if (int e = b2_recon_loss_terms(a.sdef + off1, a.tar + off1, velp, m0, a.loss_terms + 2 * p0, np, H, W, stream)) return e;
   }
   return B2_OK;
 }

@@ -43,7 +43,8 @@ __device__ __forceinline__ int mirror_q(int g, int q) { return g == 0 ? q : (q ^
 struct ClusterParams {
   b2_shoot_args a;
   float* scratch;        // per cluster: [u ping | u pong | m0] + bins; the spectrum exchange reuses the next-u field
-  int64_t P;
+  int64_t P;                // pairs of the whole batch (trajectory strides)
+  int64_t p0, p1;           // pairs this launch processes: [p0, p1)
   int64_t cluster_stride;   // floats of scratch per cluster
 };
 
@@ -271,7 +272,7 @@ shoot_cluster_kernel(const ClusterParams prm) {
   const int pc = c_group_block[rk][q] * 16 + cc;        // global spectrum cell column
   __syncthreads();
 
-  for (int64_t p = blockIdx.x / kCL; p < prm.P; p += ncl) {
+  for (int64_t p = prm.p0 + blockIdx.x / kCL; p < prm.p1; p += ncl) {
     float* base = prm.scratch + (size_t)(blockIdx.x / kCL) * prm.cluster_stride;
     float* ubuf0 = base;
     float* ubuf1 = ubuf0 + 2 * (size_t)N;
@@ -558,12 +559,15 @@ int64_t cluster_workspace_bytes(int64_t P) {
 
 int launch_shoot_cluster(const b2_shoot_args& a, void* workspace, cudaStream_t st) {
   const int64_t P = a.B * a.T1;
-  const int ncl = cluster_grid_clusters(P);
+  const int64_t p0 = a.pair_count > 0 ? a.pair_begin : 0, np = a.pair_count > 0 ? a.pair_count : P;
+  const int ncl = cluster_grid_clusters(np);
   if (ncl < 1) return B2_E_FFTSIZE;
   ClusterParams prm;
   prm.a = a;
   prm.scratch = reinterpret_cast<float*>(workspace);
   prm.P = P;
+  prm.p0 = p0;
+  prm.p1 = p0 + np;
   prm.cluster_stride = (int64_t)cluster_scratch_floats();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(kCL * ncl));

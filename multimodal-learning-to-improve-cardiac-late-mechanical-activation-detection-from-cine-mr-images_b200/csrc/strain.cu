@@ -51,14 +51,14 @@ sector_map_kernel(const long long* __restrict__ mom, const b2_sector_frame fr, i
 __global__ void __launch_bounds__(kNTS)
 strain_sector_fwd_kernel(const float* __restrict__ u, const float* __restrict__ tar, const long long* __restrict__ mom,
                          const b2_sector_frame fr, float* __restrict__ S, int32_t* __restrict__ counts,
-                         int B, int T1, int H, int W, int n_sectors, int n_frames) {
+                         int B, int T1, int H, int W, int n_sectors, int n_frames, long long p0, long long p1) {
   extern __shared__ __align__(8) unsigned long long smem_q[];
   unsigned long long* sums_s = smem_q;                                   // n_sectors x u64
   int32_t* tab_s = reinterpret_cast<int32_t*>(smem_q + n_sectors);       // 2 n_sectors x i32
   int* cnts_s = tab_s + 2 * n_sectors;                                   // n_sectors x i32
   const int tid = threadIdx.x;
   const int N = H * W;
-  for (long long pt = blockIdx.x; pt < (long long)B * T1; pt += gridDim.x) {
+  for (long long pt = p0 + blockIdx.x; pt < p1; pt += gridDim.x) {
     const int b = (int)(pt / T1), t = (int)(pt % T1);
     const SectorFrame f = sector_frame_of(fr.table, fr.table_slice_stride, fr.theta0, fr.clockwise, b);
     __syncthreads();
@@ -173,20 +173,32 @@ extern "C" int b2_strain_sector_fwd(const float* u, const float* tar, const int6
   return b2_strain_sector_fwd_ex(u, tar, moments, &fr, S, counts, B, T1, H, W, n_sectors, n_frames, stream);
 }
 
-extern "C" int b2_strain_sector_fwd_ex(const float* u, const float* tar, const int64_t* moments,
-                                       const b2_sector_frame* frame, float* S, int32_t* counts, int64_t B, int64_t T1,
-                                       int64_t H, int64_t W, int n_sectors, int n_frames, void* stream) {
+// Pairs [p0, p0 + np) of the batch only (all pointers address the whole batch): the op-level arm of b2_shoot_fwd with
+// a pair range (shoot.cu).
+namespace b2 {
+int strain_sector_fwd_range(const float* u, const float* tar, const int64_t* moments, const b2_sector_frame* frame,
+                            float* S, int32_t* counts, int64_t B, int64_t T1, int64_t H, int64_t W, int n_sectors,
+                            int n_frames, int64_t p0, int64_t np, cudaStream_t st) {
   if (!u || !tar || !moments || !frame || !frame->table || !S) return B2_E_NULL;
   if (frame->table_slice_stride < 0) return B2_E_PARAM;
   if (int e = check_strain(B, T1, H, W, n_sectors, n_frames)) return e;
-  cudaStream_t st = (cudaStream_t)stream;
-  int64_t grid = B * T1;
+  if (p0 < 0 || np <= 0 || p0 + np > B * T1) return B2_E_SHAPE;
+  int64_t grid = np;
   if (grid > (1 << 20)) grid = 1 << 20;
   strain_sector_fwd_kernel<<<(unsigned)grid, kNTS, sizeof(int32_t) * 5 * n_sectors, st>>>(
       u, tar, reinterpret_cast<const long long*>(moments), *frame, S, counts, (int)B, (int)T1, (int)H, (int)W,
-      n_sectors, n_frames);
+      n_sectors, n_frames, (long long)p0, (long long)(p0 + np));
   B2_CHECK_LAUNCH();
   return B2_OK;
+}
+}  // namespace b2
+
+extern "C" int b2_strain_sector_fwd_ex(const float* u, const float* tar, const int64_t* moments,
+                                       const b2_sector_frame* frame, float* S, int32_t* counts, int64_t B, int64_t T1,
+                                       int64_t H, int64_t W, int n_sectors, int n_frames, void* stream) {
+  if (int e = check_strain(B, T1, H, W, n_sectors, n_frames)) return e;
+  return strain_sector_fwd_range(u, tar, moments, frame, S, counts, B, T1, H, W, n_sectors, n_frames, 0, B * T1,
+                                 (cudaStream_t)stream);
 }
 
 extern "C" int b2_strain_sector_bwd(const float* gS, const float* u, const float* tar, const int64_t* moments,

@@ -37,6 +37,8 @@ fuse_seeds = True
 # units of one cluster's time per pair (measured on B200); the split minimises the longer arm.
 idle_sm_split = True
 idle_sm_pair_cost = 0.23
+idle_sm_pair_granular = True      # cut the batch at a pair, not at a slice boundary (_idle_split_pairs)
+idle_sm_pair_cost_concurrent = 0.27   # op-level pair on 16 idle SMs WHILE the cluster kernel runs, in cluster rounds
 _side_streams = {}
 _cluster_occ = {}
 
@@ -108,14 +110,39 @@ def _idle_split_slices(B, T1, dev):
     return best if best_t <= 0.97 * whole else 0
 
 
-def _launch_shoot_split(b2, v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
+def _idle_split_pairs(B, T1, dev, b2):
+    """Refine the slice-granular split ``b2`` (:func:`_idle_split_slices`) to PAIR granularity: the number of trailing
+    frame-pairs for the op-level arm.  A slice is 1.5 cluster rounds at configs[3] (49 pairs on 33 clusters), so whole
+    slices leave one arm up to a round and a half behind; ``b2_shoot_args.pair_begin / pair_count`` lets the two arms
+    cut a slice anywhere (strain-matrix columns are written per pair).  Rule (``tools/sweep_idle_split.py``, DESIGN.md
+    section 6): the fewest cluster rounds C for which the op-level arm still ends inside the cluster arm
+    (``idle_sm_pair_cost_concurrent`` rounds per pair while the cluster kernel runs), and for that C the fewest
+    op-level pairs, P - 33 C."""
+    occ = _cluster_occ.get(dev.index)
+    if not idle_sm_pair_granular or occ is None or occ[0] < 1 or occ[1] < 4:
+        return b2 * T1
+    ncl, idle = occ
+    cost = idle_sm_pair_cost_concurrent * 16.0 / idle
+    P = B * T1
+    best = 0
+    for rounds in range(math.ceil(P / ncl) - 1, 0, -1):
+        p2 = P - rounds * ncl
+        if p2 > P // 2 or cost * p2 > rounds:
+            break
+        best = p2
+    return best if best > 0 else b2 * T1
+
+
+def _launch_shoot_split(P2, v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
                         B, T1, want, src_per_pair, src_ss, tar_ss):
-    """256x256 inference with the last ``b2`` slices on the op-level path (second stream, idle SMs); the outputs are
-    one set of slice-major tensors, each arm writes its own rows.  ``src`` / ``tar``: the strided cine views."""
+    """256x256 inference with the last ``P2`` frame-pairs on the op-level path (second stream, idle SMs); the outputs
+    are one set of slice-major tensors, each arm writes its own pairs (``pair_begin`` / ``pair_count`` of
+    ``b2_shoot_args``; the cut may fall inside a slice).  ``src`` / ``tar``: the strided cine views."""
     P, _, H, W = v0.shape
     dev = v0.device
     out = _alloc_outputs(P, B, T1, H, W, dev, want, False, n_sectors, n_frames, num_steps, False)
-    B1 = B - b2
+    P1 = P - P2
+    bs = P1 // T1                                    # first slice the op-level arm touches (whole or in part)
 
     def rows(lo, hi):
         return {k: (t[lo:hi] if k in ("S", "counts") else t[lo * T1:hi * T1]) for k, t in out.items()}
@@ -125,24 +152,25 @@ def _launch_shoot_split(b2, v0, src, tar, moments, frame, metric, num_steps, T, 
     if side is None:
         side = _side_streams[dev.index] = torch.cuda.Stream(dev)
     ready = cur.record_event()                       # inputs complete
-    _launch_shoot(v0[:B1 * T1], src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
-                  B1, T1, want, False, src_per_pair, False, out=rows(0, B1), src_slice_stride=src_ss,
-                  tar_slice_stride=tar_ss)
+    _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
+                  B, T1, want, False, src_per_pair, False, out=out, src_slice_stride=src_ss,
+                  tar_slice_stride=tar_ss, pair_range=(0, P1))
     side.wait_event(ready)
     with torch.cuda.stream(side):
-        src2 = src[B1:].reshape(b2 * T1, 1, H, W).contiguous() if src_per_pair else src[B1:].contiguous()
-        tar2 = tar[B1:].reshape(b2 * T1, 1, H, W).contiguous()
-        mom2 = moments[B1:].contiguous() if moments is not None else None
-        _launch_shoot(v0[B1 * T1:], src2, tar2, mom2, frame, metric, num_steps, T, background, n_sectors, n_frames,
-                      b2, T1, want, False, src_per_pair, False, out=rows(B1, B), first_slice=B1,
-                      flags=_lib.FLAG_OPLEVEL)
+        nb = B - bs
+        src2 = src[bs:].reshape(nb * T1, 1, H, W).contiguous() if src_per_pair else src[bs:].contiguous()
+        tar2 = tar[bs:].reshape(nb * T1, 1, H, W).contiguous()
+        mom2 = moments[bs:].contiguous() if moments is not None else None
+        _launch_shoot(v0[bs * T1:], src2, tar2, mom2, frame, metric, num_steps, T, background, n_sectors, n_frames,
+                      nb, T1, want, False, src_per_pair, False, out=rows(bs, B), first_slice=bs,
+                      flags=_lib.FLAG_OPLEVEL, pair_range=(P1 - bs * T1, P2))
     cur.wait_stream(side)
     return out
 
 
 def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background, n_sectors, n_frames,
                   B, T1, want, v0_is_momentum, src_per_pair, save_traj, out=None, ws=None,
-                  src_slice_stride=0, tar_slice_stride=0, first_slice=0, flags=None):
+                  src_slice_stride=0, tar_slice_stride=0, first_slice=0, flags=None, pair_range=None):
     """Run ``b2_shoot_fwd``; outputs are allocated here unless ``out`` (contiguous tensors) is given.
     ``frame``: :class:`strain.Frame` of the batch (``first_slice`` = offset of this launch's slices in it) or None.
     The caller has made the tensors' device current (``_lib.device_guard`` / ``on_device``)."""
@@ -158,6 +186,8 @@ def _launch_shoot(v0, src, tar, moments, frame, metric, num_steps, T, background
         fs = frame.c_struct(first_slice)
         a.table, a.table_slice_stride, a.theta0, a.clockwise = fs.table, fs.table_slice_stride, fs.theta0, fs.clockwise
     a.flags = _flags["fwd"] if flags is None else flags
+    if pair_range is not None and tuple(pair_range) != (0, P):      # (begin, count) of the batch's pairs
+        a.pair_begin, a.pair_count = int(pair_range[0]), int(pair_range[1])
     for k in ("m0", "vel", "u", "sdef", "S", "counts", "traj", "loss_terms"):
         setattr(a, k, out[k].data_ptr() if k in out else None)
     a.B, a.T1, a.H, a.W = B, T1, H, W
@@ -271,7 +301,7 @@ class ShootWarpStrainFunction(torch.autograd.Function):
         b2 = _idle_split_slices(B, T1, v0.device) if (H == 256 and _fused_size(H, W) and not need and src_ss
                                                       and not torch.cuda.is_current_stream_capturing()) else 0
         if b2:
-            out = _launch_shoot_split(b2, v0, src, tar, moments if with_strain else None,
+            out = _launch_shoot_split(_idle_split_pairs(B, T1, v0.device, b2), v0, src, tar, moments if with_strain else None,
                                       frame if with_strain else None, metric, num_steps, T, background, n_sectors,
                                       n_frames, B, T1, want, src_per_pair, src_ss, tar_ss)
         else:

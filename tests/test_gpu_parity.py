@@ -700,6 +700,44 @@ def test_new_entry_points_reject_bad_arguments(pkg, dev):
                                    False, False)
 
 
+def test_pair_range_of_shoot_args(pkg, oracle, dev):
+    """``pair_begin`` / ``pair_count`` of b2_shoot_args: a launch processes only its pairs and leaves the rest of the
+    batch's outputs untouched; two ranged launches (op-level path, rectangular grid; the cut inside a slice) add up
+    to the unranged result bit for bit; bad ranges and the single-CTA fused sizes are refused."""
+    sh = pkg.shooting
+    m = pkg.FluidMetric(PARAMS)
+    B, T, H, W, S = 2, 4, 64, 128, 3
+    T1 = T - 1
+    src_vol, tar_vol = _masks(pkg, B, T, H, W)
+    src, tar = src_vol[:, :, 0].contiguous().to(dev), tar_vol.reshape(B * T1, 1, H, W).contiguous().to(dev)
+    mom = pkg.strain.mask_moments(src[:, 0].contiguous())
+    frame = pkg.strain.Frame(126, B, dev)
+    v0 = _smooth_v0(pkg, B * T1, H, W, 71, 2.5).to(dev)
+    want = {"m0": True, "vel": True, "sdef": True, "S": True, "loss_terms": True}
+
+    def run(out=None, rng=None):
+        return sh._launch_shoot(v0, src, tar, mom, frame, m, S, 1.0, 0, 126, 40, B, T1, want, False, False, False,
+                                out=out, pair_range=rng)
+    full = run()
+    part = {k: torch.full_like(t, -7) for k, t in full.items()}
+    run(part, (0, 2))                                   # pairs 0, 1 of slice 0
+    torch.cuda.synchronize()
+    assert torch.equal(part["u"][:2], full["u"][:2]) and bool((part["u"][2:] == -7).all())
+    assert bool((part["sdef"][2:] == -7).all()) and bool((part["S"][1] == -7).all())
+    assert torch.equal(part["S"][0, 0, :, :2], full["S"][0, 0, :, :2]) and bool((part["S"][0, 0, :, 2:] == -7).all())
+    run(part, (2, 4))                                   # the rest: pair 2 of slice 0 and the whole slice 1
+    torch.cuda.synchronize()
+    for k in full:
+        assert torch.equal(part[k], full[k]), k
+    for bad in ((0, 7), (5, 2), (-1, 2), (3, 0)):
+        with pytest.raises(RuntimeError):
+            run(part, bad)
+    v64 = torch.zeros(2, 2, 64, 64, device=dev)         # single-CTA fused kernel: no pair ranges
+    with pytest.raises(RuntimeError):
+        sh._launch_shoot(v64, None, None, None, None, m, 2, 1.0, 0, 126, 40, 2, 1, {}, False, False, False,
+                         pair_range=(0, 1))
+
+
 def test_cluster_path_reads_cine_volume_in_place(pkg, dev):
     """256x256: strided views of one cine volume (no pair construction) give the same bits as dense copies."""
     B, T, H, W, S = 2, 3, 256, 256, 2
@@ -1441,31 +1479,42 @@ def test_idle_sm_split_matches_unsplit_and_oracle(pkg, oracle, dev, shared_src):
         src_vol = src_vol.contiguous()
     v0 = _smooth_v0(pkg, B * (T - 1), H, H, 5, 3.0)
     th, cw = [0.0, 0.7, -1.1], [True, False, True]
-    saved = sh._idle_split_slices
+    saved, saved_pairs = sh._idle_split_slices, sh._idle_split_pairs
     outs = {}
     try:
-        for b2 in (0, 1):
+        # 0 = unsplit; 1 = the last slice (3 pairs) on the op-level arm; then cuts INSIDE a slice (pair ranges of
+        # b2_shoot_args): the last 2, 4 and 1 of the 9 pairs
+        for case, (b2, p2) in enumerate(((0, 0), (1, 3), (1, 2), (1, 4), (1, 1))):
             sh._idle_split_slices = (lambda n: (lambda B_, T1_, dev_: n))(b2)
+            sh._idle_split_pairs = (lambda n: (lambda B_, T1_, dev_, b2_: n))(p2)
             with torch.no_grad():
-                outs[b2] = pkg.shoot_warp_strain(v0.to(dev), src_vol, tar_vol, pkg.FluidMetric(PARAMS), num_steps=S,
-                                                 loss_terms=True, theta0=th, clockwise=cw)
+                outs[case] = pkg.shoot_warp_strain(v0.to(dev), src_vol, tar_vol, pkg.FluidMetric(PARAMS), num_steps=S,
+                                                   loss_terms=True, theta0=th, clockwise=cw)
         torch.cuda.synchronize()
     finally:
-        sh._idle_split_slices = saved
+        sh._idle_split_slices, sh._idle_split_pairs = saved, saved_pairs
     keys = ("momentum", "velocity", "displacement", "deformed_source", "strain_matrix", "registration_loss_terms")
     # the warped source is a BINARY mask: its error is |du| in pixels times a unit jump (3e-5 as in the multi-wave test);
     # the squared-error term of the loss sums it over the image
     tol = {"deformed_source": 3e-5, "registration_loss_terms": 3e-5}
-    for k in keys:
-        assert relerr(outs[1][k], outs[0][k]) < tol.get(k, TOL), f"{k}: {relerr(outs[1][k], outs[0][k]):.2e}"
+    for case in (1, 2, 3, 4):
+        for k in keys:
+            assert relerr(outs[case][k], outs[0][k]) < tol.get(k, TOL), f"{case} {k}: {relerr(outs[case][k], outs[0][k]):.2e}"
+        assert torch.equal(outs[case]["strain_matrix"].isfinite(), outs[0]["strain_matrix"].isfinite())
     ref = oracle.forward_volume(v0, src_vol.cpu(), tar_vol.cpu(), oracle.FluidMetric(PARAMS), S, theta0=th, clockwise=cw)
     for k in keys[:5]:
         assert relerr(outs[1][k], ref[k]) < tol.get(k, TOL), f"{k} vs oracle: {relerr(outs[1][k], ref[k]):.2e}"
         assert relerr(outs[1][k][-1:], ref[k][-1:]) < tol.get(k, TOL), f"{k} (op-level arm) vs oracle"
+    for case in (2, 3, 4):                                   # mid-slice cuts: the op-level arm's pairs vs the oracle
+        for k in keys[:5]:
+            assert relerr(outs[case][k], ref[k]) < tol.get(k, TOL), f"{case} {k} vs oracle"
     # the planner: nothing to split for one slice or a batch that fills whole rounds; a real share otherwise
     assert sh._idle_split_slices(1, 49, dev) == 0
     b2 = sh._idle_split_slices(256, 49, dev)
     assert 0 <= b2 <= 64
+    if b2:
+        p2 = sh._idle_split_pairs(256, 49, dev, b2)
+        assert 0 < p2 <= 256 * 49 // 2
     # a differentiable call never splits (the adjoint needs the trajectory of every pair in one layout)
     vg = v0.to(dev).requires_grad_(True)
     sh._idle_split_slices = lambda *a: (_ for _ in ()).throw(AssertionError("split consulted on the training path"))

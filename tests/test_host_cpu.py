@@ -87,6 +87,19 @@ def test_idle_sm_split_planner(pkg):
         assert sh._idle_split_slices(1, 49, dev) == 0
         for B in range(2, 40):
             assert 0 <= sh._idle_split_slices(B, 24, dev) <= B // 2
+        # pair granularity: whole cluster rounds on the cluster arm, the op-level arm ends inside them, and the cut
+        # the sweep on the device found best (58 of 784 pairs, 149 of 1568)
+        import math
+        assert sh._idle_split_pairs(16, 49, dev, 2) == 58 and sh._idle_split_pairs(32, 49, dev, 3) == 149
+        for B in (16, 32, 64, 256):
+            b2 = sh._idle_split_slices(B, 49, dev)
+            p2 = sh._idle_split_pairs(B, 49, dev, b2)
+            rounds = (B * 49 - p2) // 33
+            assert 0 < p2 <= B * 49 // 2 and (B * 49 - p2) % 33 == 0
+            assert 0.27 * p2 <= rounds < math.ceil(B * 49 / 33)
+        sh.idle_sm_pair_granular = False
+        assert sh._idle_split_pairs(16, 49, dev, 2) == 98
+        sh.idle_sm_pair_granular = True
         sh._cluster_occ[0] = (37, 0)              # a device whose GPCs pack whole clusters: nothing to gain
         assert sh._idle_split_slices(64, 49, dev) == 0
         sh._cluster_occ[0] = (0, 0)               # clusters unavailable

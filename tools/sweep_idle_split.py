@@ -2,7 +2,7 @@
 """Calibrate `shooting.idle_sm_pair_cost`: time the 256x256 inference batch with b2 = 0, 1, 2, ... trailing slices on
 the op-level path (second stream, the SMs the 4-CTA clusters strand) and print ms per step for each.
 
-  python tools/sweep_idle_split.py [slices] [b2 values, comma separated]
+  python tools/sweep_idle_split.py [slices] [b2 values, comma separated] [P2 values (trailing PAIRS), comma separated]
 """
 import json
 import pathlib
@@ -35,9 +35,18 @@ def main():
     for b2 in b2s:
         sh._idle_split_slices = (lambda n: (lambda B_, T1_, dev_: n))(b2)
         res[str(b2)] = round(bc.timed(step, 3, 1), 3)
-    sh._idle_split_slices = auto
+    res_p = {}
+    auto_p = sh._idle_split_pairs
+    if len(sys.argv) > 3:                      # cuts at pair granularity (pair ranges of b2_shoot_args)
+        sh._idle_split_slices = lambda B_, T1_, dev_: 1
+        for p2 in [int(x) for x in sys.argv[3].split(",")]:
+            sh._idle_split_pairs = (lambda n: (lambda B_, T1_, dev_, b2_: n))(p2)
+            res_p[str(p2)] = round(bc.timed(step, 3, 1), 3)
+    sh._idle_split_slices, sh._idle_split_pairs = auto, auto_p
     res["auto"] = round(bc.timed(step, 3, 1), 3)
-    print(json.dumps({"slices": B, "pairs": B * (T - 1), "ms_by_b2": res, "auto_b2": auto(B, T - 1, dev)}))
+    b2 = auto(B, T - 1, dev)
+    print(json.dumps({"slices": B, "pairs": B * (T - 1), "ms_by_b2": res, "ms_by_p2": res_p, "auto_b2": b2,
+                      "auto_p2": auto_p(B, T - 1, dev, b2) if b2 else 0}))
 
 
 if __name__ == "__main__":
