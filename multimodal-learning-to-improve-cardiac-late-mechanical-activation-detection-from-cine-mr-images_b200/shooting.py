@@ -617,12 +617,12 @@ class HostPipeline:
                     st["v0"][: nb * T1].copy_(v0_host[b0 * T1: b1 * T1], non_blocking=True)
                     self.h2d_bytes += nb * T1 * 2 * H * W * 4
                     n = nb * T * H * W
-                    src_u8 = None
+                    # the copy stream carries copies only (back-to-back DMA); narrow masks are widened on the compute
+                    # stream in front of the kernel that reads them
+                    src_u8, widen = None, None
                     if bit_masks:
                         st["vol_u8"][: n // 8].copy_(vol_host[b0:b1].reshape(-1), non_blocking=True)
-                        check(lib().b2_unpack_bits(ptr(st["vol_u8"]), ptr(st["vol"]), n,
-                                                   C.c_void_p(self.copy_stream.cuda_stream)), "b2_unpack_bits")
-                        _lib.count_launch()
+                        widen = lib().b2_unpack_bits
                         self.h2d_bytes += n // 8
                     elif byte_masks:
                         src_u8 = vol_host[b0:b1].reshape(-1)
@@ -632,15 +632,16 @@ class HostPipeline:
                         pass
                     elif src_u8 is not None:
                         st["vol_u8"][:n].copy_(src_u8[:n], non_blocking=True)
-                        check(lib().b2_unpack_u8(ptr(st["vol_u8"]), ptr(st["vol"]), n,
-                                                 C.c_void_p(self.copy_stream.cuda_stream)), "b2_unpack_u8")
-                        _lib.count_launch()
+                        widen = lib().b2_unpack_u8
                         self.h2d_bytes += n
                     else:
                         st["vol"][:nb].copy_(vol_host[b0:b1], non_blocking=True)
                         self.h2d_bytes += n * 4
                     st["ready"].record(self.copy_stream)
                 main.wait_event(st["ready"])
+                if widen is not None:
+                    check(widen(ptr(st["vol_u8"]), ptr(st["vol"]), n, C.c_void_p(main.cuda_stream)), "b2_unpack")
+                    _lib.count_launch()
                 vol = st["vol"][:nb]                                     # (nb,1,T,H,W): read in place by the kernel
                 mom = mask_moments(vol[:, 0, 0].contiguous())
                 sl = slice(b0 * T1, b1 * T1)
